@@ -1,0 +1,120 @@
+/* snarkb200.h — C ABI of libsnarkb200.so, the B200 (sm_100a) backend for snarkjs' bulk curve operations.
+ *
+ * Every entry point replaces one async method of the ffjavascript `curve` object that snarkjs' provers call
+ * (SURVEY.md §8b).  Citations are into /root/reference/build/snarkjs.js (first bundled copy of
+ * ffjavascript@0.3.1) unless a src/ path is given.  INTEGRATION.md shows the N-API shim that binds them.
+ *
+ * Conventions
+ *   - all pointers are HOST memory unless the name ends in _dev; buffers are little-endian;
+ *   - field elements are 32 bytes (Fr, BN254 Fq) or 48 bytes (BLS12-381 Fq);
+ *     "Montgomery" = x*2^(8*n8) mod p, fully reduced (reference 2873-2874, 3263-3272);
+ *   - G1 affine = x||y (2*n8q), G2 affine = x.c0||x.c1||y.c0||y.c1 (4*n8q), infinity = all-zero bytes;
+ *   - MSM output = Jacobian X||Y||Z Montgomery (3*n8q / 6*n8q), normalised to Z = 1 (infinity = (0,1,0));
+ *     the reference returns an arbitrary projective representative, only its toAffine() is defined (§3.3);
+ *   - return 0 on success, negative on error; sb_last_error(ctx) gives the message — the JS shim throws
+ *     `new Error(msg)` so that error strings match the reference's;
+ *   - the callee never retains caller memory (reference: inputs are sliced/copied, 14645-14646, 14739);
+ *   - a context is bound to one CUDA device; calls on one context are serialised by the caller
+ *     (one context per thread / per GPU).
+ */
+#ifndef SNARKB200_H
+#define SNARKB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb_ctx sb_ctx;
+enum { SB_BN254 = 0, SB_BLS12_381 = 1 };
+enum { SB_G1 = 1, SB_G2 = 2 };
+enum {
+    SB_OK = 0,
+    SB_ERR_ARG = -1,        /* bad argument (message mirrors the reference's Error text) */
+    SB_ERR_CUDA = -2,       /* CUDA runtime error */
+    SB_ERR_NOMEM = -3,
+    SB_ERR_FORMAT = -4,     /* malformed zkey / wtns */
+    SB_ERR_NODEVICE = -5    /* no CUDA device: the library never falls back to the CPU */
+};
+
+/* buildBn128 / buildBls12381 + buildEngine (16413-16523, 15433-15490): one context per curve and device. */
+int  sb_create(int curve, int device_id, sb_ctx** out);
+void sb_destroy(sb_ctx* ctx);                       /* curve.terminate() 14259-14264 */
+const char* sb_last_error(sb_ctx* ctx);
+const char* sb_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t sb_launch_count(sb_ctx* ctx);
+
+/* G1.multiExpAffine / G2.multiExpAffine (14666-14668 -> _multiExp 14605-14661).
+ * n = number of points; scalar_bytes = bytes per scalar (the reference infers it as byteLength/n and throws
+ * "Scalar size does not match" when not integral, 14562-14565 — the shim performs that check).
+ * n == 0 -> zero point (14561, 14627). */
+int sb_msm_g1_affine(sb_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, uint32_t scalar_bytes, uint64_t n, uint8_t* out);
+int sb_msm_g2_affine(sb_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, uint32_t scalar_bytes, uint64_t n, uint8_t* out);
+
+/* Read-only base sets (zkey sections 5-9, PLONK/fflonk PTau) registered once and kept in HBM across proofs. */
+int sb_bases_register(sb_ctx* ctx, int group, const uint8_t* bases, uint64_t n, uint64_t* handle);
+int sb_bases_release(sb_ctx* ctx, uint64_t handle);
+/* MSM over registered bases [first, first+n) with host scalars. */
+int sb_msm_registered(sb_ctx* ctx, uint64_t handle, uint64_t first, const uint8_t* scalars, uint32_t scalar_bytes, uint64_t n, uint8_t* out);
+/* Same, additionally returning the un-normalised extended-Jacobian partial (X,Y,ZZ,ZZZ; 4 or 8 coordinates) that
+ * sb_msm_sum_partials combines — the exchange unit of the multi-GPU MSM (one rank per GPU). */
+int sb_msm_registered_partial(sb_ctx* ctx, uint64_t handle, uint64_t first, const uint8_t* scalars, uint32_t scalar_bytes, uint64_t n, uint8_t* partial_out);
+int sb_msm_sum_partials(sb_ctx* ctx, int group, const uint8_t* partials, int count, uint8_t* out);
+uint32_t sb_msm_partial_bytes(sb_ctx* ctx, int group);
+
+/* Fr.fft / Fr.ifft (15101-15107 -> _fft 14675-14918).  n must be a power of two ("fft must be multiple of 2",
+ * 14745-14747) with log2(n) <= Fr.s (28 / 32).  Natural order in and out; inverse != 0 scales by 1/n. */
+int sb_ntt_fr(sb_ctx* ctx, const uint8_t* in, uint64_t n, int inverse, uint8_t* out);
+/* Fr.batchApplyKey (14273-14384 / frm_batchApplyKey 9458): out[i] = in[i] * first * inc^i. */
+int sb_fr_batch_apply_key(sb_ctx* ctx, const uint8_t* in, uint64_t n, const uint8_t first[32], const uint8_t inc[32], uint8_t* out);
+/* Fr.batchToMontgomery / Fr.batchFromMontgomery (12895-12896 -> 12780-12830). */
+int sb_fr_batch_to_montgomery(sb_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out);
+int sb_fr_batch_from_montgomery(sb_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out);
+/* tm.queueAction([qap_joinABC, frm_batchFromMontgomery]) as used by joinABC, src/groth16_prove.js:320-374:
+ * out[i] = fromMontgomery(a[i]*b[i] - c[i]). */
+int sb_qap_join_abc(sb_ctx* ctx, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint64_t n, uint8_t* out_plain);
+/* Fr constants the JS side reads from the curve object: what = -1 -> Fr.shift (nqr^2), -2 -> Fr.nqr,
+ * 0..s -> Fr.w[what] (12866-12889).  Returns s. */
+int sb_fr_root(sb_ctx* ctx, int what, uint8_t out[32]);
+
+/* Fused Groth16 prover (src/groth16_prove.js:28-144) with every intermediate resident in HBM.
+ * sb_groth16_load parses a Groth16 .zkey image (src/zkey_utils.js:229-259 + sections 4-9), uploads the five base
+ * sets and a CSR form of the coefficient section once.  sb_groth16_prove takes the witness section payload
+ * (n_witness * 32 bytes, plain LE, src/wtns_utils.js:25-37) and (r, s) as 32-byte Montgomery Fr elements (the
+ * reference draws them with Fr.random(), :103-104), and writes the affine proof pi_a (2*n8q) || pi_b (4*n8q) ||
+ * pi_c (2*n8q), Montgomery.  public signals are witness[1..nPublic]. */
+int sb_groth16_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handle);
+int sb_groth16_load_file(sb_ctx* ctx, const char* zkey_path, uint64_t* handle);
+int sb_groth16_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size);
+int sb_groth16_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness,
+                     const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
+/* full file-to-proof convenience: reads the .wtns container, checks curve and length like the reference (:44-50). */
+int sb_groth16_prove_wtns(sb_ctx* ctx, uint64_t handle, const uint8_t* wtns, uint64_t wtns_len,
+                          const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
+int sb_groth16_release(sb_ctx* ctx, uint64_t handle);
+/* multi-GPU: this rank proves with its shard [shard, n_shards) of every MSM and returns the five un-normalised
+ * MSM partials (A, B1, C, H in G1; B2 in G2) instead of a proof; the ranks exchange them (NCCL all-gather) and any
+ * rank finishes with sb_groth16_finish. */
+int sb_groth16_prove_shard(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness,
+                           int shard, int n_shards, uint8_t* partials_out);
+uint32_t sb_groth16_partials_bytes(sb_ctx* ctx);
+int sb_groth16_finish(sb_ctx* ctx, uint64_t handle, const uint8_t* partials_all_ranks, int n_shards,
+                      const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
+
+/* Device-resident variants (inputs already in HBM): what bench.py's `value` times.  Pointers are device pointers
+ * in this context's device; out is host memory. */
+int sb_msm_dev(sb_ctx* ctx, int group, const void* bases_dev, const void* scalars_dev, uint32_t scalar_bytes, uint64_t n, uint8_t* out);
+int sb_ntt_fr_dev(sb_ctx* ctx, void* data_dev, void* scratch_dev, uint64_t n, int inverse, void** result_dev);
+void* sb_dev_alloc(sb_ctx* ctx, uint64_t bytes);
+int sb_dev_free(sb_ctx* ctx, void* p);
+int sb_dev_upload(sb_ctx* ctx, void* dst_dev, const uint8_t* src, uint64_t bytes);
+int sb_dev_download(sb_ctx* ctx, uint8_t* dst, const void* src_dev, uint64_t bytes);
+/* timing of the last call on this context, measured with CUDA events on the context's stream (ms):
+ * which = 0 total device time of the call, 1.. = per-stage breakdown where the call defines one. */
+float sb_last_ms(sb_ctx* ctx, int which);
+int sb_sync(sb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,771 @@
+// api.cu — the C ABI of libsnarkb200.so (include/snarkb200.h): context, device buffers, table caches, the
+// drop-in bulk operations, and the fused Groth16 prover.  Host-side orchestration only; kernels live in
+// msm*.cu / fr_kernels.cu.  There is no CPU fallback: without a CUDA device sb_create fails.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include <mutex>
+#include "../../include/snarkb200.h"
+#include "ec.cuh"
+#include "msm.cuh"
+#include "msm_entry.h"
+#include "fr_entry.h"
+
+using namespace sb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes > cap) { if (p) cudaFree(p); p = nullptr; cap = 0; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; cap = bytes; }
+        return p;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// group vtable (one per curve x group)
+struct GroupOps {
+    int (*buckets)(const void*, const MsmSorted&, MsmScratch&, cudaStream_t, void*, MsmLaunchStats*);
+    void (*combine)(const uint8_t*, const MsmGeom&, uint8_t*);
+    void (*add)(uint8_t*, const uint8_t*);
+    void (*to_jacobian)(const uint8_t*, uint8_t*);
+    void (*to_affine)(const uint8_t*, uint8_t*);
+    void (*from_affine)(const uint8_t*, uint8_t*);
+    void (*times)(const uint8_t*, const uint8_t*, int, uint8_t*);
+    uint32_t xyzz_bytes;
+    uint32_t aff_bytes;
+};
+#define SB_GROUP_OPS(NAME, AFF) GroupOps{NAME##_buckets, NAME##_combine, NAME##_add, NAME##_to_jacobian, NAME##_to_affine, NAME##_from_affine, NAME##_times, NAME##_xyzz_bytes(), AFF}
+
+struct NttTab { DevBuf lo, hi; int h = 0; };
+struct PreTab { DevBuf lo, hi; int h = 0; std::string key; };
+
+struct BaseSet { int group = 0; uint64_t n = 0; void* d = nullptr; };
+
+struct Groth16Key {
+    uint32_t nVars = 0, nPublic = 0, domainSize = 0; int power = 0;
+    std::vector<uint8_t> alpha1, beta1, beta2, gamma2, delta1, delta2;
+    void *dA = nullptr, *dB1 = nullptr, *dB2 = nullptr, *dC = nullptr, *dH = nullptr;   // bases (C padded to nVars)
+    uint64_t* d_rowptr = nullptr; uint32_t* d_sig = nullptr; void* d_coef = nullptr; uint64_t nCoef = 0;
+    // device work buffers
+    void *dW = nullptr, *dA_T = nullptr, *dB_T = nullptr, *dC_T = nullptr, *dTmp = nullptr, *dWsum = nullptr;
+};
+
+}  // namespace
+
+struct sb_ctx {
+    int curve = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint32_t n8q = 32;
+    GroupOps g1, g2;
+    MsmScratch sort_scratch, bucket_scratch;
+    MsmLaunchStats stats;
+    uint64_t launches = 0;
+    DevBuf io[4];
+    std::map<int, NttTab> ntt_fwd, ntt_inv;
+    DevBuf wr_fwd, wr_inv;
+    std::map<int, DevBuf> ninv;           // n^-1 per L
+    std::vector<PreTab*> pre_cache;
+    std::vector<BaseSet> bases;
+    std::vector<Groth16Key*> keys;
+    cudaEvent_t ev[8];
+    float last_ms[8] = {0};
+    int fr_s = 0;
+    std::vector<std::vector<uint8_t>> roots;   // w[0..s] Montgomery bytes
+    std::vector<uint8_t> nqr, shift;
+};
+
+namespace {
+
+int fail(sb_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+int cuda_fail(sb_ctx* c, cudaError_t e, const char* where) {
+    return fail(c, e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CU(c, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(c, _e, #call); } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// host Fr helpers, templated on the scalar-field tag
+// ------------------------------------------------------------------------------------------------------------
+template <class P> struct HostFr {
+    typedef Fp<P> F;
+    static F from_u32(uint32_t x) { F a = F::zero(); a.v[0] = x; return F::to_mont(a); }
+    static void roots(int& s, std::vector<F>& w, F& nqr, F& shift) {
+        // reference 12866-12889: nqr = first non-residue from 2, s = 2-adicity, w[s] = nqr^((r-1)/2^s), w[i] = w[i+1]^2
+        const int N = P::N;
+        uint32_t pm1[N]; for (int i = 0; i < N; i++) pm1[i] = P::p(i); pm1[0] -= 1;
+        uint32_t half[N]; for (int i = 0; i < N; i++) half[i] = (pm1[i] >> 1) | (i + 1 < N ? pm1[i + 1] << 31 : 0);
+        F negone = F::neg(F::one());
+        nqr = from_u32(2);
+        while (!(F::pow(nqr, half, N) == negone)) nqr = F::add(nqr, F::one());
+        shift = F::sqr(nqr);
+        uint32_t t[N]; memcpy(t, pm1, sizeof t); s = 0;
+        while (!(t[0] & 1)) { for (int i = 0; i < N; i++) t[i] = (t[i] >> 1) | (i + 1 < N ? t[i + 1] << 31 : 0); s++; }
+        w.assign(s + 1, F::zero());
+        w[s] = F::pow(nqr, t, N);
+        for (int i = s - 1; i >= 0; i--) w[i] = F::sqr(w[i + 1]);
+    }
+    // lo[e] = base^e (e < 2^h), hi[e] = scale * (base^(2^h))^e (e < nhi)
+    static void pow_tables(const F& base, const F& scale, int h, uint64_t nhi, std::vector<F>& lo, std::vector<F>& hi) {
+        lo.resize((size_t)1 << h); hi.resize(nhi ? nhi : 1);
+        F t = F::one();
+        for (size_t e = 0; e < lo.size(); e++) { lo[e] = t; t = F::mul(t, base); }
+        F step = t;   // base^(2^h)
+        t = scale;
+        for (size_t e = 0; e < hi.size(); e++) { hi[e] = t; t = F::mul(t, step); }
+    }
+};
+
+template <class P> int init_roots(sb_ctx* c) {
+    typedef Fp<P> F;
+    std::vector<F> w; F nqr, shift; int s;
+    HostFr<P>::roots(s, w, nqr, shift);
+    c->fr_s = s;
+    c->roots.resize(s + 1);
+    for (int i = 0; i <= s; i++) c->roots[i].assign((uint8_t*)&w[i], (uint8_t*)&w[i] + 32);
+    c->nqr.assign((uint8_t*)&nqr, (uint8_t*)&nqr + 32);
+    c->shift.assign((uint8_t*)&shift, (uint8_t*)&shift + 32);
+    // in-tile roots w_{2^DMAX}^j and inverse
+    F wd = w[NTT_DMAX], wdi = F::inv(wd);
+    std::vector<F> lo, hi;
+    HostFr<P>::pow_tables(wd, F::one(), NTT_DMAX - 1, 1, lo, hi);
+    if (!c->wr_fwd.get(lo.size() * 32)) return SB_ERR_NOMEM;
+    cudaMemcpy(c->wr_fwd.p, lo.data(), lo.size() * 32, cudaMemcpyHostToDevice);
+    HostFr<P>::pow_tables(wdi, F::one(), NTT_DMAX - 1, 1, lo, hi);
+    if (!c->wr_inv.get(lo.size() * 32)) return SB_ERR_NOMEM;
+    cudaMemcpy(c->wr_inv.p, lo.data(), lo.size() * 32, cudaMemcpyHostToDevice);
+    return 0;
+}
+
+template <class P> int build_ntt_tab(sb_ctx* c, int L, bool inverse, NttTab& tab) {
+    typedef Fp<P> F;
+    F w; memcpy(&w, c->roots[L].data(), 32);
+    if (inverse) w = F::inv(w);
+    int h = (L + 1) / 2;
+    std::vector<F> lo, hi;
+    HostFr<P>::pow_tables(w, F::one(), h, (uint64_t)1 << (L - h), lo, hi);
+    tab.h = h;
+    if (!tab.lo.get(lo.size() * 32) || !tab.hi.get(hi.size() * 32)) return SB_ERR_NOMEM;
+    cudaMemcpy(tab.lo.p, lo.data(), lo.size() * 32, cudaMemcpyHostToDevice);
+    cudaMemcpy(tab.hi.p, hi.data(), hi.size() * 32, cudaMemcpyHostToDevice);
+    return 0;
+}
+
+int get_ntt_tab(sb_ctx* c, int L, bool inverse, FrNttTables* out) {
+    auto& m = inverse ? c->ntt_inv : c->ntt_fwd;
+    auto it = m.find(L);
+    if (it == m.end()) {
+        NttTab& t = m[L];
+        int rc = c->curve == SB_BN254 ? build_ntt_tab<BnFr>(c, L, inverse, t) : build_ntt_tab<BlsFr>(c, L, inverse, t);
+        if (rc) { m.erase(L); return fail(c, rc, "ntt table allocation failed"); }
+        it = m.find(L);
+    }
+    out->tw_lo = it->second.lo.p; out->tw_hi = it->second.hi.p; out->h = it->second.h;
+    out->wr = inverse ? c->wr_inv.p : c->wr_fwd.p;
+    return 0;
+}
+
+template <class P> void ninv_bytes(int L, uint8_t* out) {
+    typedef Fp<P> F;
+    F two = F::add(F::one(), F::one()), n = F::one();
+    for (int i = 0; i < L; i++) n = F::mul(n, two);
+    F r = F::inv(n); memcpy(out, &r, 32);
+}
+const void* get_ninv(sb_ctx* c, int L) {
+    auto it = c->ninv.find(L);
+    if (it == c->ninv.end()) {
+        uint8_t b[32];
+        if (c->curve == SB_BN254) ninv_bytes<BnFr>(L, b); else ninv_bytes<BlsFr>(L, b);
+        DevBuf& d = c->ninv[L];
+        if (!d.get(32)) return nullptr;
+        cudaMemcpy(d.p, b, 32, cudaMemcpyHostToDevice);
+        it = c->ninv.find(L);
+    }
+    return it->second.p;
+}
+
+// apply-key tables for (n, first, inc): lo[e] = inc^e, hi[e] = first * inc^(e 2^h)
+template <class P> int build_pre(sb_ctx* c, uint64_t n, const uint8_t* first, const uint8_t* inc, PreTab& t) {
+    typedef Fp<P> F;
+    int bits = 0; while (((uint64_t)1 << bits) < n) bits++;
+    int h = (bits + 1) / 2;
+    F f, i; memcpy(&f, first, 32); memcpy(&i, inc, 32);
+    std::vector<F> lo, hi;
+    HostFr<P>::pow_tables(i, f, h, (n + ((uint64_t)1 << h) - 1) >> h, lo, hi);
+    t.h = h;
+    if (!t.lo.get(lo.size() * 32) || !t.hi.get(hi.size() * 32)) return SB_ERR_NOMEM;
+    cudaMemcpy(t.lo.p, lo.data(), lo.size() * 32, cudaMemcpyHostToDevice);
+    cudaMemcpy(t.hi.p, hi.data(), hi.size() * 32, cudaMemcpyHostToDevice);
+    return 0;
+}
+int get_pre(sb_ctx* c, uint64_t n, const uint8_t* first, const uint8_t* inc, FrPre* out) {
+    std::string key((const char*)&n, 8); key.append((const char*)first, 32); key.append((const char*)inc, 32);
+    for (PreTab* t : c->pre_cache) if (t->key == key) { out->lo = t->lo.p; out->hi = t->hi.p; out->h = t->h; return 0; }
+    PreTab* t = new PreTab(); t->key = key;
+    int rc = c->curve == SB_BN254 ? build_pre<BnFr>(c, n, first, inc, *t) : build_pre<BlsFr>(c, n, first, inc, *t);
+    if (rc) { delete t; return fail(c, rc, "apply-key table allocation failed"); }
+    if (c->pre_cache.size() >= 16) { delete c->pre_cache.front(); c->pre_cache.erase(c->pre_cache.begin()); }
+    c->pre_cache.push_back(t);
+    out->lo = t->lo.p; out->hi = t->hi.p; out->h = t->h;
+    return 0;
+}
+
+void tick(sb_ctx* c, int i) { cudaEventRecord(c->ev[i], c->stream); }
+float elapsed(sb_ctx* c, int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; }
+
+// ------------------------------------------------------------------------------------------------------------
+// MSM over device-resident bases/scalars: sort once, one bucket pipeline, host recombination.
+// acc (host XYZZ bytes) += result
+// ------------------------------------------------------------------------------------------------------------
+int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const uint8_t* d_scalars, uint32_t sbytes, uint64_t n,
+                       uint8_t* acc_xyzz) {
+    static const uint64_t MAXC = 1ull << 23;
+    for (uint64_t off = 0; off < n; off += MAXC) {
+        uint64_t cn = std::min(MAXC, n - off);
+        MsmGeom g = msm_geometry(cn, sbytes);
+        MsmSorted s;
+        int rc = msm_sort_entries(d_scalars + off * sbytes, sbytes, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
+        void* d_wsum = c->io[3].get((size_t)g.W * G.xyzz_bytes);
+        if (!d_wsum) return fail(c, SB_ERR_NOMEM, "out of device memory");
+        rc = G.buckets((const uint8_t*)d_bases + off * G.aff_bytes, s, c->bucket_scratch, c->stream, d_wsum, &c->stats);
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
+        std::vector<uint8_t> ws((size_t)g.W * G.xyzz_bytes);
+        CU(c, cudaMemcpyAsync(ws.data(), d_wsum, ws.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        G.combine(ws.data(), g, acc_xyzz);
+    }
+    return 0;
+}
+
+int msm_host_inputs(sb_ctx* c, int group, const uint8_t* bases, const void* d_bases_opt, const uint8_t* scalars, uint32_t sbytes,
+                    uint64_t n, uint8_t* out_jac, uint8_t* out_partial) {
+    if (!c) return SB_ERR_ARG;
+    const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
+    std::vector<uint8_t> acc(G.xyzz_bytes, 0);
+    if (n) {
+        if (sbytes == 0 || sbytes > 64) return fail(c, SB_ERR_ARG, "Scalar size does not match");
+        cudaSetDevice(c->device);
+        tick(c, 0);
+        const void* d_bases = d_bases_opt;
+        if (!d_bases) {
+            void* p = c->io[0].get(n * G.aff_bytes);
+            if (!p) return fail(c, SB_ERR_NOMEM, "out of device memory");
+            CU(c, cudaMemcpyAsync(p, bases, n * G.aff_bytes, cudaMemcpyHostToDevice, c->stream));
+            d_bases = p;
+        }
+        uint8_t* d_sc = (uint8_t*)c->io[1].get(n * sbytes);
+        if (!d_sc) return fail(c, SB_ERR_NOMEM, "out of device memory");
+        CU(c, cudaMemcpyAsync(d_sc, scalars, n * sbytes, cudaMemcpyHostToDevice, c->stream));
+        tick(c, 1);
+        int rc = msm_dev_accumulate(c, G, d_bases, d_sc, sbytes, n, acc.data());
+        if (rc) return rc;
+        tick(c, 2);
+        cudaEventSynchronize(c->ev[2]);
+        c->last_ms[0] = elapsed(c, 0, 2); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2);
+    }
+    if (out_partial) memcpy(out_partial, acc.data(), acc.size());
+    if (out_jac) G.to_jacobian(acc.data(), out_jac);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// binfile / zkey parsing (@iden3/binfileutils readBinFile 17468-17498; src/zkey_utils.js:229-259)
+// ------------------------------------------------------------------------------------------------------------
+struct Section { uint64_t pos = 0, len = 0; bool present = false; };
+int parse_binfile(sb_ctx* c, const uint8_t* d, uint64_t len, const char* magic, uint32_t max_version, std::map<uint32_t, Section>& secs) {
+    if (len < 12 || memcmp(d, magic, 4) != 0) return fail(c, SB_ERR_FORMAT, std::string(magic) + ": Invalid File format");
+    uint32_t ver, nsec; memcpy(&ver, d + 4, 4); memcpy(&nsec, d + 8, 4);
+    if (ver > max_version) return fail(c, SB_ERR_FORMAT, "Version not supported");
+    uint64_t pos = 12;
+    for (uint32_t i = 0; i < nsec; i++) {
+        if (pos + 12 > len) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        uint32_t id; uint64_t sl; memcpy(&id, d + pos, 4); memcpy(&sl, d + pos + 4, 8); pos += 12;
+        if (pos + sl > len) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        if (secs[id].present) return fail(c, SB_ERR_FORMAT, "Section Duplicated " + std::to_string(id));
+        secs[id].pos = pos; secs[id].len = sl; secs[id].present = true;
+        pos += sl;
+    }
+    if (pos != len) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+    return 0;
+}
+
+bool modulus_matches(const uint8_t* p, uint32_t n8, int curve, bool scalar_field) {
+    uint32_t limbs[12] = {0};
+    if (curve == SB_BN254) { if (n8 != 32) return false; for (int i = 0; i < 8; i++) limbs[i] = scalar_field ? BnFr::p(i) : BnFq::p(i); }
+    else if (scalar_field) { if (n8 != 32) return false; for (int i = 0; i < 8; i++) limbs[i] = BlsFr::p(i); }
+    else { if (n8 != 48) return false; for (int i = 0; i < 12; i++) limbs[i] = BlsFq::p(i); }
+    return memcmp(p, limbs, n8) == 0;
+}
+
+void free_key(Groth16Key* k) {
+    for (void* p : {k->dA, k->dB1, k->dB2, k->dC, k->dH, (void*)k->d_rowptr, (void*)k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, k->dTmp, k->dWsum})
+        if (p) cudaFree(p);
+    delete k;
+}
+
+template <class PR> static void fr_from_mont_bytes(const uint8_t* in, uint8_t* out) { Fp<PR> a; memcpy(&a, in, 32); a = Fp<PR>::from_mont(a); memcpy(out, &a, 32); }
+template <class PR> static void fr_neg_mul_bytes(const uint8_t* r, const uint8_t* s, uint8_t* out) { Fp<PR> a, b; memcpy(&a, r, 32); memcpy(&b, s, 32); a = Fp<PR>::neg(Fp<PR>::mul(a, b)); memcpy(out, &a, 32); }
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+const char* sb_version(void) { return "snarkb200 0.1 (sm_100a)"; }
+
+int sb_create(int curve, int device_id, sb_ctx** out) {
+    if (!out || (curve != SB_BN254 && curve != SB_BLS12_381)) return SB_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SB_ERR_NODEVICE;
+    if (device_id < 0 || device_id >= ndev) return SB_ERR_ARG;
+    if (cudaSetDevice(device_id) != cudaSuccess) return SB_ERR_CUDA;
+    sb_ctx* c = new sb_ctx();
+    c->curve = curve; c->device = device_id;
+    c->n8q = curve == SB_BN254 ? 32 : 48;
+    if (curve == SB_BN254) { c->g1 = SB_GROUP_OPS(bn254_g1, 64); c->g2 = SB_GROUP_OPS(bn254_g2, 128); }
+    else { c->g1 = SB_GROUP_OPS(bls12381_g1, 96); c->g2 = SB_GROUP_OPS(bls12381_g2, 192); }
+    if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return SB_ERR_CUDA; }
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    int rc = curve == SB_BN254 ? init_roots<BnFr>(c) : init_roots<BlsFr>(c);
+    if (rc == 0 && fr_configure(curve) != 0) rc = SB_ERR_CUDA;
+    if (rc) { sb_destroy(c); return rc; }
+    *out = c;
+    return SB_OK;
+}
+
+void sb_destroy(sb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto* k : c->keys) if (k) free_key(k);
+    for (auto& b : c->bases) if (b.d) cudaFree(b.d);
+    for (auto* t : c->pre_cache) { t->lo.release(); t->hi.release(); delete t; }
+    for (auto& kv : c->ntt_fwd) { kv.second.lo.release(); kv.second.hi.release(); }
+    for (auto& kv : c->ntt_inv) { kv.second.lo.release(); kv.second.hi.release(); }
+    for (auto& kv : c->ninv) kv.second.release();
+    c->wr_fwd.release(); c->wr_inv.release();
+    for (auto& b : c->io) b.release();
+    c->sort_scratch.release(); c->bucket_scratch.release();
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* sb_last_error(sb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+uint64_t sb_launch_count(sb_ctx* c) { return c ? c->launches + (uint64_t)c->stats.launches : 0; }
+float sb_last_ms(sb_ctx* c, int which) { return (c && which >= 0 && which < 8) ? c->last_ms[which] : 0.f; }
+int sb_sync(sb_ctx* c) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+
+int sb_msm_g1_affine(sb_ctx* c, const uint8_t* bases, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
+    return msm_host_inputs(c, SB_G1, bases, nullptr, scalars, sb, n, out, nullptr);
+}
+int sb_msm_g2_affine(sb_ctx* c, const uint8_t* bases, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
+    return msm_host_inputs(c, SB_G2, bases, nullptr, scalars, sb, n, out, nullptr);
+}
+
+int sb_bases_register(sb_ctx* c, int group, const uint8_t* bases, uint64_t n, uint64_t* handle) {
+    if (!c || !handle || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
+    const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
+    BaseSet b; b.group = group; b.n = n;
+    CU(c, cudaMalloc(&b.d, n ? n * G.aff_bytes : 16));
+    CU(c, cudaMemcpy(b.d, bases, n * G.aff_bytes, cudaMemcpyHostToDevice));
+    c->bases.push_back(b);
+    *handle = c->bases.size();
+    return 0;
+}
+int sb_bases_release(sb_ctx* c, uint64_t h) {
+    if (!c || h == 0 || h > c->bases.size() || !c->bases[h - 1].d) return fail(c, SB_ERR_ARG, "invalid bases handle");
+    cudaSetDevice(c->device);
+    cudaFree(c->bases[h - 1].d); c->bases[h - 1].d = nullptr; c->bases[h - 1].n = 0;
+    return 0;
+}
+static int msm_registered_impl(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out, uint8_t* partial) {
+    if (!c || h == 0 || h > c->bases.size() || !c->bases[h - 1].d) return fail(c, SB_ERR_ARG, "invalid bases handle");
+    const BaseSet& b = c->bases[h - 1];
+    if (first + n > b.n) return fail(c, SB_ERR_ARG, "registered base range out of bounds");
+    const GroupOps& G = b.group == SB_G1 ? c->g1 : c->g2;
+    return msm_host_inputs(c, b.group, nullptr, (const uint8_t*)b.d + first * G.aff_bytes, scalars, sb, n, out, partial);
+}
+int sb_msm_registered(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
+    return msm_registered_impl(c, h, first, scalars, sb, n, out, nullptr);
+}
+int sb_msm_registered_partial(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* partial) {
+    return msm_registered_impl(c, h, first, scalars, sb, n, nullptr, partial);
+}
+uint32_t sb_msm_partial_bytes(sb_ctx* c, int group) { return c ? (group == SB_G1 ? c->g1.xyzz_bytes : c->g2.xyzz_bytes) : 0; }
+int sb_msm_sum_partials(sb_ctx* c, int group, const uint8_t* partials, int count, uint8_t* out) {
+    if (!c || (group != SB_G1 && group != SB_G2) || count < 0) return SB_ERR_ARG;
+    const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
+    std::vector<uint8_t> acc(G.xyzz_bytes, 0);
+    for (int i = 0; i < count; i++) G.add(acc.data(), partials + (size_t)i * G.xyzz_bytes);
+    G.to_jacobian(acc.data(), out);
+    return 0;
+}
+
+int sb_msm_dev(sb_ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint32_t sb, uint64_t n, uint8_t* out) {
+    if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
+    const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
+    std::vector<uint8_t> acc(G.xyzz_bytes, 0);
+    tick(c, 0);
+    if (n) { int rc = msm_dev_accumulate(c, G, bases_dev, (const uint8_t*)scalars_dev, sb, n, acc.data()); if (rc) return rc; }
+    tick(c, 1); cudaEventSynchronize(c->ev[1]); c->last_ms[0] = elapsed(c, 0, 1);
+    G.to_jacobian(acc.data(), out);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- Fr ops
+static int ntt_dev(sb_ctx* c, void* a, void* b, uint64_t n, int inverse, const FrPre* pre, bool scale, void** result) {
+    if (n == 0 || (n & (n - 1))) return fail(c, SB_ERR_ARG, "fft must be multiple of 2");
+    int L = 0; while (((uint64_t)1 << L) < n) L++;
+    if (L > c->fr_s) return fail(c, SB_ERR_ARG, "fft size exceeds the 2-adicity of Fr (fftExt path not supported)");
+    if (L == 0) { *result = a; return 0; }
+    FrNttTables tb;
+    int rc = get_ntt_tab(c, L, inverse != 0, &tb); if (rc) return rc;
+    const void* post = nullptr;
+    if (inverse && scale) { post = get_ninv(c, L); if (!post) return fail(c, SB_ERR_NOMEM, "out of device memory"); }
+    int launches = 0;
+    rc = fr_ntt(c->curve, a, b, L, &tb, pre, post, c->stream, result, &launches);
+    c->launches += launches;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt");
+    return 0;
+}
+
+int sb_ntt_fr(sb_ctx* c, const uint8_t* in, uint64_t n, int inverse, uint8_t* out) {
+    if (!c) return SB_ERR_ARG;
+    if (n == 0 || (n & (n - 1))) return fail(c, SB_ERR_ARG, "fft must be multiple of 2");
+    cudaSetDevice(c->device);
+    void* a = c->io[0].get(n * 32); void* b = c->io[1].get(n * 32);
+    if (!a || !b) return fail(c, SB_ERR_NOMEM, "out of device memory");
+    tick(c, 0);
+    CU(c, cudaMemcpyAsync(a, in, n * 32, cudaMemcpyHostToDevice, c->stream));
+    tick(c, 1);
+    void* res = nullptr;
+    int rc = ntt_dev(c, a, b, n, inverse, nullptr, true, &res); if (rc) return rc;
+    tick(c, 2);
+    CU(c, cudaMemcpyAsync(out, res, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    tick(c, 3);
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->last_ms[0] = elapsed(c, 0, 3); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2); c->last_ms[3] = elapsed(c, 2, 3);
+    return 0;
+}
+int sb_ntt_fr_dev(sb_ctx* c, void* data, void* scratch, uint64_t n, int inverse, void** result) {
+    if (!c || !result) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
+    tick(c, 0);
+    int rc = ntt_dev(c, data, scratch, n, inverse, nullptr, true, result); if (rc) return rc;
+    tick(c, 1);
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->last_ms[0] = elapsed(c, 0, 1);
+    return 0;
+}
+
+int sb_fr_batch_apply_key(sb_ctx* c, const uint8_t* in, uint64_t n, const uint8_t first[32], const uint8_t inc[32], uint8_t* out) {
+    if (!c) return SB_ERR_ARG;
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    FrPre pre; int rc = get_pre(c, n, first, inc, &pre); if (rc) return rc;
+    void* a = c->io[0].get(n * 32); void* b = c->io[1].get(n * 32);
+    if (!a || !b) return fail(c, SB_ERR_NOMEM, "out of device memory");
+    CU(c, cudaMemcpyAsync(a, in, n * 32, cudaMemcpyHostToDevice, c->stream));
+    rc = fr_apply_key(c->curve, a, b, n, &pre, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_apply_key");
+    CU(c, cudaMemcpyAsync(out, b, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int convert_impl(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, int to_mont) {
+    if (!c) return SB_ERR_ARG;
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    void* a = c->io[0].get(n * 32); void* b = c->io[1].get(n * 32);
+    if (!a || !b) return fail(c, SB_ERR_NOMEM, "out of device memory");
+    CU(c, cudaMemcpyAsync(a, in, n * 32, cudaMemcpyHostToDevice, c->stream));
+    int rc = fr_convert(c->curve, a, b, n, to_mont, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_convert");
+    CU(c, cudaMemcpyAsync(out, b, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sb_fr_batch_to_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { return convert_impl(c, in, n, out, 1); }
+int sb_fr_batch_from_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { return convert_impl(c, in, n, out, 0); }
+
+int sb_qap_join_abc(sb_ctx* c, const uint8_t* a, const uint8_t* b, const uint8_t* cc, uint64_t n, uint8_t* out) {
+    if (!c) return SB_ERR_ARG;
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    void* da = c->io[0].get(n * 32); void* db = c->io[1].get(n * 32); void* dc = c->io[2].get(n * 32); void* dout = c->io[3].get(n * 32);
+    if (!da || !db || !dc || !dout) return fail(c, SB_ERR_NOMEM, "out of device memory");
+    CU(c, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dc, cc, n * 32, cudaMemcpyHostToDevice, c->stream));
+    int rc = fr_join_abc(c->curve, da, db, dc, dout, n, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_join_abc");
+    CU(c, cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) {
+    if (!c) return SB_ERR_ARG;
+    if (what == -1) memcpy(out, c->shift.data(), 32);
+    else if (what == -2) memcpy(out, c->nqr.data(), 32);
+    else if (what >= 0 && what <= c->fr_s) memcpy(out, c->roots[what].data(), 32);
+    else return fail(c, SB_ERR_ARG, "root index out of range");
+    return c->fr_s;
+}
+
+void* sb_dev_alloc(sb_ctx* c, uint64_t bytes) { if (!c) return nullptr; cudaSetDevice(c->device); void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; return p; }
+int sb_dev_free(sb_ctx* c, void* p) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaFree(p)); return 0; }
+int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+
+// ---------------------------------------------------------------------------------------------------- Groth16
+int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) {
+    if (!c || !z || !handle) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
+    std::map<uint32_t, Section> secs;
+    int rc = parse_binfile(c, z, zlen, "zkey", 2, secs); if (rc) return rc;
+    for (uint32_t id : {1u, 2u, 4u, 5u, 6u, 7u, 8u, 9u}) if (!secs[id].present) return fail(c, SB_ERR_FORMAT, "Missing section " + std::to_string(id));
+    uint32_t proto; memcpy(&proto, z + secs[1].pos, 4);
+    if (proto != 1) return fail(c, SB_ERR_FORMAT, "zkey file is not groth16");
+    const uint8_t* h = z + secs[2].pos; uint64_t hl = secs[2].len;
+    const uint32_t n8q = c->n8q, n8r = 32;
+    const uint64_t need = 4 + n8q + 4 + n8r + 12 + 3 * 2 * n8q + 3 * 4 * n8q;
+    if (hl < need) return fail(c, SB_ERR_FORMAT, "zkey header too short");
+    uint32_t v; memcpy(&v, h, 4);
+    if (v != n8q || !modulus_matches(h + 4, n8q, c->curve, false)) return fail(c, SB_ERR_FORMAT, "zkey curve does not match the context curve");
+    memcpy(&v, h + 4 + n8q, 4);
+    if (v != n8r || !modulus_matches(h + 8 + n8q, n8r, c->curve, true)) return fail(c, SB_ERR_FORMAT, "zkey curve does not match the context curve");
+    Groth16Key* k = new Groth16Key();
+    const uint8_t* q = h + 8 + n8q + n8r;
+    memcpy(&k->nVars, q, 4); memcpy(&k->nPublic, q + 4, 4); memcpy(&k->domainSize, q + 8, 4); q += 12;
+    const uint32_t sG1 = 2 * n8q, sG2 = 4 * n8q;
+    k->alpha1.assign(q, q + sG1); q += sG1; k->beta1.assign(q, q + sG1); q += sG1;
+    k->beta2.assign(q, q + sG2); q += sG2; k->gamma2.assign(q, q + sG2); q += sG2;
+    k->delta1.assign(q, q + sG1); q += sG1; k->delta2.assign(q, q + sG2);
+    const uint64_t n = k->domainSize, nv = k->nVars;
+    if (n == 0 || (n & (n - 1))) { delete k; return fail(c, SB_ERR_FORMAT, "domain size is not a power of two"); }
+    while (((uint64_t)1 << k->power) < n) k->power++;
+    if (k->power > c->fr_s) { delete k; return fail(c, SB_ERR_FORMAT, "Circuit too big for this curve"); }
+    if (nv < (uint64_t)k->nPublic + 1) { delete k; return fail(c, SB_ERR_FORMAT, "invalid zkey header"); }
+    if (secs[5].len != nv * sG1 || secs[6].len != nv * sG1 || secs[7].len != nv * sG2 ||
+        secs[8].len != (nv - k->nPublic - 1) * sG1 || secs[9].len != n * sG1) { delete k; return fail(c, SB_ERR_FORMAT, "zkey section size mismatch"); }
+    // coefficient section -> CSR over rows (matrix m, constraint c): src/zkey_utils.js:110-118, groth16_prove.js:147-187
+    uint32_t ncoef; memcpy(&ncoef, z + secs[4].pos, 4);
+    const uint64_t sCoef = 12 + n8r;
+    if (secs[4].len != 4 + ncoef * sCoef) { delete k; return fail(c, SB_ERR_FORMAT, "zkey coefficient section size mismatch"); }
+    const uint8_t* cf = z + secs[4].pos + 4;
+    std::vector<uint64_t> rowptr(2 * n + 1, 0);
+    for (uint64_t i = 0; i < ncoef; i++) {
+        uint32_t m, cc, s; memcpy(&m, cf + i * sCoef, 4); memcpy(&cc, cf + i * sCoef + 4, 4); memcpy(&s, cf + i * sCoef + 8, 4);
+        if (m > 1 || cc >= n || s >= nv) { delete k; return fail(c, SB_ERR_FORMAT, "zkey coefficient out of range"); }
+        rowptr[m * n + cc + 1]++;
+    }
+    for (uint64_t i = 0; i < 2 * n; i++) rowptr[i + 1] += rowptr[i];
+    std::vector<uint64_t> cursor(rowptr.begin(), rowptr.end() - 1);
+    std::vector<uint32_t> sig(ncoef ? ncoef : 1); std::vector<uint8_t> coef((size_t)(ncoef ? ncoef : 1) * 32);
+    for (uint64_t i = 0; i < ncoef; i++) {
+        uint32_t m, cc, s; memcpy(&m, cf + i * sCoef, 4); memcpy(&cc, cf + i * sCoef + 4, 4); memcpy(&s, cf + i * sCoef + 8, 4);
+        uint64_t p = cursor[m * n + cc]++;
+        sig[p] = s; memcpy(&coef[p * 32], cf + i * sCoef + 12, 32);
+    }
+    k->nCoef = ncoef;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void** d, const void* src, size_t bytes, size_t alloc) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(d, alloc ? alloc : 16); if (e != cudaSuccess) return;
+        if (bytes) e = cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up(&k->dA, z + secs[5].pos, nv * sG1, nv * sG1);
+    up(&k->dB1, z + secs[6].pos, nv * sG1, nv * sG1);
+    up(&k->dB2, z + secs[7].pos, nv * sG2, nv * sG2);
+    // C bases are indexed by signal - (nPublic+1): pad so that one sorted digit list of the witness serves A, B1, B2 and C
+    if (e == cudaSuccess) {
+        e = cudaMalloc(&k->dC, nv * sG1);
+        if (e == cudaSuccess) e = cudaMemset(k->dC, 0, (size_t)(k->nPublic + 1) * sG1);
+        if (e == cudaSuccess && secs[8].len) e = cudaMemcpy((uint8_t*)k->dC + (size_t)(k->nPublic + 1) * sG1, z + secs[8].pos, secs[8].len, cudaMemcpyHostToDevice);
+    }
+    up(&k->dH, z + secs[9].pos, n * sG1, n * sG1);
+    up((void**)&k->d_rowptr, rowptr.data(), rowptr.size() * 8, rowptr.size() * 8);
+    up((void**)&k->d_sig, sig.data(), (size_t)ncoef * 4, (size_t)ncoef * 4);
+    up(&k->d_coef, coef.data(), (size_t)ncoef * 32, (size_t)ncoef * 32);
+    up(&k->dW, nullptr, 0, nv * 32);
+    up(&k->dA_T, nullptr, 0, n * 32); up(&k->dB_T, nullptr, 0, n * 32); up(&k->dC_T, nullptr, 0, n * 32); up(&k->dTmp, nullptr, 0, n * 32);
+    up(&k->dWsum, nullptr, 0, 8 * 80 * 4 * 96);
+    if (e != cudaSuccess) { free_key(k); return cuda_fail(c, e, "sb_groth16_load upload"); }
+    c->keys.push_back(k);
+    *handle = c->keys.size();
+    return 0;
+}
+
+int sb_groth16_load_file(sb_ctx* c, const char* path, uint64_t* handle) {
+    if (!c || !path) return SB_ERR_ARG;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, SB_ERR_FORMAT, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf((size_t)sz);
+    size_t rd = fread(buf.data(), 1, (size_t)sz, f); fclose(f);
+    if (rd != (size_t)sz) return fail(c, SB_ERR_FORMAT, "short read");
+    return sb_groth16_load(c, buf.data(), buf.size(), handle);
+}
+
+static Groth16Key* get_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->keys.size()) ? c->keys[h - 1] : nullptr; }
+
+int sb_groth16_info(sb_ctx* c, uint64_t h, uint32_t* nv, uint32_t* np, uint32_t* ds) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    if (nv) *nv = k->nVars; if (np) *np = k->nPublic; if (ds) *ds = k->domainSize;
+    return 0;
+}
+int sb_groth16_release(sb_ctx* c, uint64_t h) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    cudaSetDevice(c->device); free_key(k); c->keys[h - 1] = nullptr; return 0;
+}
+uint32_t sb_groth16_partials_bytes(sb_ctx* c) { return c ? 4 * c->g1.xyzz_bytes + c->g2.xyzz_bytes : 0; }
+
+// device part of the prover: returns the five MSM partials (A, B1, C, H | B2) as host XYZZ bytes.
+static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials) {
+    if (n_witness != k->nVars) return fail(c, SB_ERR_ARG, "Invalid witness length. Circuit: " + std::to_string(k->nVars) + ", witness: " + std::to_string(n_witness));
+    cudaSetDevice(c->device);
+    const uint64_t n = k->domainSize, nv = k->nVars;
+    const int cv = c->curve;
+    int rc;
+    tick(c, 0);
+    CU(c, cudaMemcpyAsync(k->dW, witness, nv * 32, cudaMemcpyHostToDevice, c->stream));
+    tick(c, 1);
+    // buildABC1 (:147-187)
+    rc = fr_qap_rows(cv, k->d_rowptr, k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, n, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_qap_rows");
+    // :64-76  ifft -> batchApplyKey(1, inc) -> fft, with 1/n of the inverse folded into the coset table
+    const uint8_t* inc = (k->power == c->fr_s) ? c->shift.data() : c->roots[k->power + 1].data();
+    uint8_t ninv[32];
+    if (cv == SB_BN254) ninv_bytes<BnFr>(k->power, ninv); else ninv_bytes<BlsFr>(k->power, ninv);
+    FrPre pre; rc = get_pre(c, n, ninv, inc, &pre); if (rc) return rc;
+    void* odd[3]; void* bufs[3] = {k->dA_T, k->dB_T, k->dC_T};
+    void* tmp = k->dTmp;
+    for (int i = 0; i < 3; i++) {
+        void* r1 = nullptr; void* r2 = nullptr;
+        rc = ntt_dev(c, bufs[i], tmp, n, 1, nullptr, false, &r1); if (rc) return rc;
+        void* other = (r1 == bufs[i]) ? tmp : bufs[i];
+        rc = ntt_dev(c, r1, other, n, 0, &pre, false, &r2); if (rc) return rc;
+        odd[i] = r2;
+        tmp = (r2 == r1) ? other : r1;   // the buffer not holding the result becomes the next scratch
+    }
+    // joinABC (:320-374) -> plain scalars for the H MSM, written over the remaining scratch buffer
+    rc = fr_join_abc(cv, odd[0], odd[1], odd[2], tmp, n, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_join_abc");
+    tick(c, 2);
+    // MSMs (:84-101).  Shard = contiguous point range; shard 0 of 1 = everything.
+    auto range = [&](uint64_t total, uint64_t& lo, uint64_t& cnt) { uint64_t per = (total + n_shards - 1) / n_shards; lo = std::min(total, per * shard); cnt = std::min(total - lo, per); };
+    const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
+    uint8_t* pA = partials; uint8_t* pB1 = pA + G1.xyzz_bytes; uint8_t* pC = pB1 + G1.xyzz_bytes; uint8_t* pH = pC + G1.xyzz_bytes; uint8_t* pB2 = pH + G1.xyzz_bytes;
+    memset(partials, 0, 4 * G1.xyzz_bytes + G2.xyzz_bytes);
+    static const uint64_t MAXC = 1ull << 23;
+    uint64_t wlo, wcnt; range(nv, wlo, wcnt);
+    for (uint64_t off = 0; off < wcnt; off += MAXC) {
+        uint64_t cn = std::min(MAXC, wcnt - off), base = wlo + off;
+        MsmGeom g = msm_geometry(cn, 32);
+        MsmSorted s;
+        rc = msm_sort_entries((const uint8_t*)k->dW + base * 32, 32, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
+        uint8_t* ws = (uint8_t*)k->dWsum;
+        size_t w1 = (size_t)g.W * G1.xyzz_bytes, w2 = (size_t)g.W * G2.xyzz_bytes;
+        if (3 * w1 + w2 > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
+        rc = G1.buckets((const uint8_t*)k->dA + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm A");
+        rc = G1.buckets((const uint8_t*)k->dB1 + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B1");
+        rc = G1.buckets((const uint8_t*)k->dC + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + 2 * w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm C");
+        rc = G2.buckets((const uint8_t*)k->dB2 + base * G2.aff_bytes, s, c->bucket_scratch, c->stream, ws + 3 * w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B2");
+        std::vector<uint8_t> hw(3 * w1 + w2);
+        CU(c, cudaMemcpyAsync(hw.data(), ws, hw.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        G1.combine(hw.data(), g, pA); G1.combine(hw.data() + w1, g, pB1); G1.combine(hw.data() + 2 * w1, g, pC); G2.combine(hw.data() + 3 * w1, g, pB2);
+    }
+    tick(c, 3);
+    uint64_t hlo, hcnt; range(n, hlo, hcnt);
+    if (hcnt) {
+        rc = msm_dev_accumulate(c, G1, (const uint8_t*)k->dH + hlo * G1.aff_bytes, (const uint8_t*)tmp + hlo * 32, 32, hcnt, pH);
+        if (rc) return rc;
+    }
+    tick(c, 4);
+    cudaEventSynchronize(c->ev[4]);
+    c->last_ms[0] = elapsed(c, 0, 4); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2); c->last_ms[3] = elapsed(c, 2, 3); c->last_ms[4] = elapsed(c, 3, 4);
+    return 0;
+}
+
+// host part: proof assembly, src/groth16_prove.js:103-132
+
+static int groth16_assemble(sb_ctx* c, Groth16Key* k, const uint8_t* partials, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+    const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
+    const uint32_t x1 = G1.xyzz_bytes, x2 = G2.xyzz_bytes;
+    std::vector<uint8_t> A(partials, partials + x1), B1(partials + x1, partials + 2 * x1), C(partials + 2 * x1, partials + 3 * x1),
+        H(partials + 3 * x1, partials + 4 * x1), B2(partials + 4 * x1, partials + 4 * x1 + x2);
+    uint8_t rp[32], sp[32], rs[32], rsp[32];
+    if (c->curve == SB_BN254) { fr_from_mont_bytes<BnFr>(r, rp); fr_from_mont_bytes<BnFr>(s, sp); fr_neg_mul_bytes<BnFr>(r, s, rs); fr_from_mont_bytes<BnFr>(rs, rsp); }
+    else { fr_from_mont_bytes<BlsFr>(r, rp); fr_from_mont_bytes<BlsFr>(s, sp); fr_neg_mul_bytes<BlsFr>(r, s, rs); fr_from_mont_bytes<BlsFr>(rs, rsp); }
+    std::vector<uint8_t> t1(x1), t2(x2), d1(x1), d2(x2), pt(x1), pt2(x2);
+    G1.from_affine(k->delta1.data(), d1.data()); G2.from_affine(k->delta2.data(), d2.data());
+    // pi_a = A + alpha1 + r*delta1
+    G1.from_affine(k->alpha1.data(), pt.data()); G1.add(A.data(), pt.data());
+    G1.times(d1.data(), rp, 32, t1.data()); G1.add(A.data(), t1.data());
+    // pi_b = B2 + beta2 + s*delta2
+    G2.from_affine(k->beta2.data(), pt2.data()); G2.add(B2.data(), pt2.data());
+    G2.times(d2.data(), sp, 32, t2.data()); G2.add(B2.data(), t2.data());
+    // pib1 = B1 + beta1 + s*delta1
+    G1.from_affine(k->beta1.data(), pt.data()); G1.add(B1.data(), pt.data());
+    G1.times(d1.data(), sp, 32, t1.data()); G1.add(B1.data(), t1.data());
+    // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1
+    G1.add(C.data(), H.data());
+    G1.times(A.data(), sp, 32, t1.data()); G1.add(C.data(), t1.data());
+    G1.times(B1.data(), rp, 32, t1.data()); G1.add(C.data(), t1.data());
+    G1.times(d1.data(), rsp, 32, t1.data()); G1.add(C.data(), t1.data());
+    G1.to_affine(A.data(), proof);
+    G2.to_affine(B2.data(), proof + G1.aff_bytes);
+    G1.to_affine(C.data(), proof + G1.aff_bytes + G2.aff_bytes);
+    return 0;
+}
+
+int sb_groth16_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
+    int rc = groth16_device(c, k, witness, n_witness, 0, 1, partials.data()); if (rc) return rc;
+    return groth16_assemble(c, k, partials.data(), r, s, proof);
+}
+int sb_groth16_prove_shard(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials_out) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(c, SB_ERR_ARG, "invalid shard");
+    return groth16_device(c, k, witness, n_witness, shard, n_shards, partials_out);
+}
+int sb_groth16_finish(sb_ctx* c, uint64_t h, const uint8_t* all, int n_shards, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
+    const uint32_t x1 = G1.xyzz_bytes, pb = sb_groth16_partials_bytes(c);
+    std::vector<uint8_t> acc(pb, 0);
+    for (int i = 0; i < n_shards; i++) {
+        const uint8_t* p = all + (size_t)i * pb;
+        for (int j = 0; j < 4; j++) G1.add(acc.data() + j * x1, p + j * x1);
+        G2.add(acc.data() + 4 * x1, p + 4 * x1);
+    }
+    return groth16_assemble(c, k, acc.data(), r, s, proof);
+}
+
+int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    std::map<uint32_t, Section> secs;
+    int rc = parse_binfile(c, w, wlen, "wtns", 2, secs); if (rc) return rc;
+    if (!secs[1].present || !secs[2].present) return fail(c, SB_ERR_FORMAT, "Missing section");
+    const uint8_t* hd = w + secs[1].pos;
+    uint32_t n8; memcpy(&n8, hd, 4);
+    if (secs[1].len < 8 + (uint64_t)n8) return fail(c, SB_ERR_FORMAT, "wtns header too short");
+    if (!modulus_matches(hd + 4, n8, c->curve, true)) return fail(c, SB_ERR_ARG, "Curve of the witness does not match the curve of the proving key");
+    uint32_t nw; memcpy(&nw, hd + 4 + n8, 4);
+    if (secs[2].len != (uint64_t)nw * n8) return fail(c, SB_ERR_FORMAT, "Invalid witness section size");
+    return sb_groth16_prove(c, h, w + secs[2].pos, nw, r, s, proof);
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// msm.cuh — Pippenger multi-scalar multiplication on one B200 (templated on the coordinate field).
+//
+// Replaces ffjavascript engine_multiexp (_multiExp/_multiExpChunk, reference build/snarkjs.js:14517-14669)
+// and wasmcurves build_multiexp (g?m_multiexpAffine_chunk 5542-5695, _getChunk 5471-5540,
+// _reduceTable 5819-5907).  The reference runs one task per (point-chunk, window), each re-copying its
+// chunk; here all windows are processed in one pass over the scalars:
+//
+//   k_digits      scalars -> signed c-bit digits; one (key = window*B + |d|-1, val = index | sign<<31)
+//                 entry per non-zero digit   (B = 2^(c-1) buckets per window)
+//   radix sort    entries by key (cub::DeviceRadixSort, library plumbing)
+//   k_accumulate  balanced segmented bucket accumulation: every thread owns SEG consecutive sorted
+//                 entries regardless of bucket sizes (robust to witness-like skew: many 0/1 scalars),
+//                 gathers affine bases with 128-bit loads, XYZZ mixed adds; a run that starts inside
+//                 the segment is written straight to its bucket, the thread's first run goes to a
+//                 "head" partial that the next (32x smaller) level folds in.
+//   k_fold        same segmented walk over the head partials (full XYZZ adds) until one thread is left
+//   k_reduce      per window sum_b (b+1)*bucket[b] by chunked running sums + small scalar multiply,
+//                 then a shared-memory tree to one point per window
+//   host          Horner over the W window sums (W*c doublings on 1 point: latency-bound, CPU is faster)
+#pragma once
+#include <cuda_runtime.h>
+#include "ec.cuh"
+#include "msm_geom.h"
+
+namespace sb {
+
+static constexpr int MSM_SEG = 32;          // sorted entries per thread in k_accumulate / k_fold
+static constexpr int MSM_ACC_THREADS = 128;
+static constexpr int MSM_RED_CHUNK = 32;    // buckets per thread in k_reduce
+static constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
+
+
+__host__ inline MsmGeom msm_geometry(uint64_t n, uint32_t scalar_bytes) {
+    int l2 = 0; while ((1ull << (l2 + 1)) <= n) l2++;
+    int c = l2 - 4; if (c < 3) c = 3; if (c > 18) c = 18;
+    MsmGeom g; g.c = c; g.W = (int)((8 * scalar_bytes + 1 + c - 1) / c); g.B = 1u << (c - 1);
+    return g;
+}
+
+template <class F> __device__ __forceinline__ void load_affine(const Affine<F>* __restrict__ bases, uint32_t idx, F& x, F& y) {
+    constexpr int NV = sizeof(F) / 16;
+    const uint4* p = reinterpret_cast<const uint4*>(bases + idx);
+    uint4* dx = reinterpret_cast<uint4*>(&x);
+    uint4* dy = reinterpret_cast<uint4*>(&y);
+#pragma unroll
+    for (int k = 0; k < NV; k++) dx[k] = __ldg(p + k);
+#pragma unroll
+    for (int k = 0; k < NV; k++) dy[k] = __ldg(p + NV + k);
+}
+template <class T> __device__ __forceinline__ void store_vec(T* dst, const T& v) {
+    constexpr int NV = sizeof(T) / 16;
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int k = 0; k < NV; k++) d[k] = s[k];
+}
+template <class T> __device__ __forceinline__ T load_vec(const T* src) {
+    constexpr int NV = sizeof(T) / 16;
+    T v; const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(&v);
+#pragma unroll
+    for (int k = 0; k < NV; k++) d[k] = s[k];
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// level 0: affine bases gathered through the sorted (key, val) list
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(MSM_ACC_THREADS)
+k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+             const uint64_t* __restrict__ counts, XYZZ<F>* __restrict__ buckets,
+             XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
+    const uint64_t M = counts[0];
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t lo = t * MSM_SEG;
+    if (lo >= M) return;
+    uint64_t hi = lo + MSM_SEG < M ? lo + MSM_SEG : M;
+    const F one = F::one();
+    XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t cur = keys[lo];
+    bool first = true;
+    for (uint64_t e = lo; e < hi; e++) {
+        uint32_t k = keys[e], v = vals[e];
+        if (k != cur) {
+            if (first) { store_vec(heads + t, acc); head_keys[t] = cur; first = false; }
+            else store_vec(buckets + cur, acc);
+            acc = XYZZ<F>::inf(); cur = k;
+        }
+        F px, py;
+        load_affine<F>(bases, v & 0x7fffffffu, px, py);
+        if (!(px.is_zero() & py.is_zero())) {          // base at infinity contributes nothing (reference 6068-6086)
+            py = F::cneg(py, (v >> 31) != 0);
+            acc.add_affine(px, py, one);
+        }
+    }
+    if (first) { store_vec(heads + t, acc); head_keys[t] = cur; }
+    else store_vec(buckets + cur, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// level >= 1: fold head partials (sorted by key by construction).  `last` = single-thread final level.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(MSM_ACC_THREADS)
+k_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, const uint64_t* __restrict__ counts, int level,
+       XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
+    const uint64_t M = counts[level];
+    const bool last = M <= MSM_SEG;
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t lo = t * MSM_SEG;
+    if (lo >= M) return;
+    uint64_t hi = lo + MSM_SEG < M ? lo + MSM_SEG : M;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t cur = in_keys[lo];
+    bool first = !last;
+    for (uint64_t e = lo; e < hi; e++) {
+        uint32_t k = in_keys[e];
+        if (k != cur) {
+            if (first) { store_vec(heads + t, acc); head_keys[t] = cur; first = false; }
+            else { XYZZ<F> b = load_vec(buckets + cur); b.add(acc); store_vec(buckets + cur, b); }
+            acc = XYZZ<F>::inf(); cur = k;
+        }
+        XYZZ<F> p = load_vec(in + e);
+        acc.add(p);
+    }
+    if (first) { store_vec(heads + t, acc); head_keys[t] = cur; }
+    else { XYZZ<F> b = load_vec(buckets + cur); b.add(acc); store_vec(buckets + cur, b); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucket reduction.  Thread (w, j) owns buckets [j*L, (j+1)*L) of window w:
+//   run = sum bucket[b],  sum = sum (b - j*L + 1) * bucket[b]   (running sums, reference _reduceTable
+//   computes the same weighted sum by recursive halving), partial = sum + (j*L) * run.
+// Then a shared-memory tree adds the partials of one CTA; CTAs of a window write to partials[w][cta].
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce(const XYZZ<F>* __restrict__ buckets, MsmGeom g, XYZZ<F>* __restrict__ partials, uint32_t ctas_per_window) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    const uint32_t w = blockIdx.x / ctas_per_window, cta = blockIdx.x % ctas_per_window;
+    const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
+    const uint32_t chunks = g.B / L;
+    const uint32_t j = cta * blockDim.x + threadIdx.x;
+    XYZZ<F> part = XYZZ<F>::inf();
+    if (j < chunks) {
+        const XYZZ<F>* bk = buckets + (uint64_t)w * g.B + (uint64_t)j * L;
+        XYZZ<F> run = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
+        for (int b = (int)L - 1; b >= 0; b--) {
+            XYZZ<F> p = load_vec(bk + b);
+            run.add(p);
+            sum.add(run);
+        }
+        // part = sum + (j*L) * run   (double-and-add, MSB first)
+        uint32_t k = j * L;
+        if (k) {
+            int top = 31 - __clz(k);
+            part = run;
+            for (int bit = top - 1; bit >= 0; bit--) {
+                part = XYZZ<F>::dbl(part);
+                if ((k >> bit) & 1) part.add(run);
+            }
+        }
+        part.add(sum);
+    }
+    store_vec(sm + threadIdx.x, part);
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            XYZZ<F> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + s);
+            a.add(b);
+            store_vec(sm + threadIdx.x, a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_vec(partials + (uint64_t)w * ctas_per_window + cta, load_vec(sm));
+}
+
+// one CTA per window: sum the per-CTA partials of k_reduce
+template <class F>
+__global__ void __launch_bounds__(32)
+k_window_sum(const XYZZ<F>* __restrict__ partials, uint32_t per_window, XYZZ<F>* __restrict__ out) {
+    if (threadIdx.x) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = 0; i < per_window; i++) { XYZZ<F> p = load_vec(partials + (uint64_t)blockIdx.x * per_window + i); acc.add(p); }
+    store_vec(out + blockIdx.x, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device scratch (grow-only) and the two halves of the pipeline.
+// ------------------------------------------------------------------------------------------------
+struct MsmScratch {
+    void* p = nullptr; size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes > cap) { if (p) cudaFree(p); p = nullptr; cap = 0; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; cap = bytes; }
+        return p;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct MsmLaunchStats { int launches = 0; };
+
+// Sorted digit entries of one scalar vector; shared by every MSM that uses the same scalars
+// (Groth16: A, B1, B2 and C all multiply the witness, src/groth16_prove.js:84-97).
+struct MsmSorted {
+    const uint32_t* keys = nullptr; const uint32_t* vals = nullptr; const uint64_t* counts = nullptr;
+    uint64_t n = 0, total = 0; MsmGeom g{};
+};
+
+// msm_sort.cu: digits + radix sort + valid count.  d_scalars is a device pointer.
+int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmGeom g, MsmScratch& scratch,
+                     cudaStream_t stream, MsmSorted* out, MsmLaunchStats* stats);
+
+// Bucket accumulation + reduction for one base set.  Writes g.W window sums to d_wsum (device).  Asynchronous.
+template <class F>
+int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream,
+                XYZZ<F>* d_wsum, MsmLaunchStats* stats) {
+    const MsmGeom g = s.g;
+    const uint64_t nbuckets = (uint64_t)g.W * g.B;
+    const uint64_t heads0 = (s.total + MSM_SEG - 1) / MSM_SEG;
+    const uint64_t heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
+    const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
+    const uint32_t chunks = g.B / L;
+    const uint32_t red_threads = 128;
+    const uint32_t ctas_per_window = (chunks + red_threads - 1) / red_threads;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_buckets = 0;
+    size_t o_headsA = o_buckets + al(nbuckets * sizeof(XYZZ<F>)), o_hkA = o_headsA + al(heads0 * sizeof(XYZZ<F>));
+    size_t o_headsB = o_hkA + al(heads0 * 4), o_hkB = o_headsB + al(heads1 * sizeof(XYZZ<F>));
+    size_t o_part = o_hkB + al(heads1 * 4);
+    size_t bytes = o_part + al((size_t)g.W * ctas_per_window * sizeof(XYZZ<F>));
+    uint8_t* base = (uint8_t*)scratch.get(bytes);
+    if (!base) return (int)cudaErrorMemoryAllocation;
+    XYZZ<F>* buckets = (XYZZ<F>*)(base + o_buckets);
+    XYZZ<F>* headsA = (XYZZ<F>*)(base + o_headsA); uint32_t* hkA = (uint32_t*)(base + o_hkA);
+    XYZZ<F>* headsB = (XYZZ<F>*)(base + o_headsB); uint32_t* hkB = (uint32_t*)(base + o_hkB);
+    XYZZ<F>* partials = (XYZZ<F>*)(base + o_part);
+    int launches = 0;
+    cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), stream);
+    if (heads0) {
+        k_accumulate<F><<<(unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
+            d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); launches++;
+        // fold cascade: level l consumes counts[l] heads (upper bound m on the host, exact count on the device)
+        uint64_t m = heads0; int level = 1;
+        XYZZ<F>* hin = headsA; uint32_t* kin = hkA; XYZZ<F>* hout = headsB; uint32_t* kout = hkB;
+        while (true) {
+            uint64_t threads = (m + MSM_SEG - 1) / MSM_SEG;
+            k_fold<F><<<(unsigned)((threads + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
+                hin, kin, s.counts, level, buckets, hout, kout); launches++;
+            if (m <= (uint64_t)MSM_SEG) break;
+            m = threads; level++;
+            XYZZ<F>* th = hin; hin = hout; hout = th; uint32_t* tk = kin; kin = kout; kout = tk;
+            if (level >= 8) return (int)cudaErrorUnknown;
+        }
+    }
+    k_reduce<F><<<g.W * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
+    k_window_sum<F><<<g.W, 32, 0, stream>>>(partials, ctas_per_window, d_wsum); launches++;
+    if (stats) stats->launches += launches;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sb

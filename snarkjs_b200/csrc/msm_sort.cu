@@ -1,0 +1,87 @@
+// msm_sort.cu — scalar recoding and bucket sort for the MSM (field independent).
+#include <cub/device/device_radix_sort.cuh>
+#include "msm.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------
+// digits: thread i recodes scalar i into W signed digits (reference _getChunk extracts unsigned chunks;
+// signed recoding halves the bucket count and is free because negating an affine point is free).
+// entries are written window-major (keys[w*n + i]) so every store is coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_digits(const uint8_t* __restrict__ scalars, uint32_t sbytes, uint64_t n, MsmGeom g,
+                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w32[17];                       // up to 64-byte scalars + 1 guard word
+    const uint8_t* s = scalars + i * sbytes;
+    if (sbytes == 32 && ((uintptr_t)scalars & 15) == 0) {
+        const uint4* p = reinterpret_cast<const uint4*>(s);
+        uint4 a = __ldg(p), b = __ldg(p + 1);
+        w32[0] = a.x; w32[1] = a.y; w32[2] = a.z; w32[3] = a.w; w32[4] = b.x; w32[5] = b.y; w32[6] = b.z; w32[7] = b.w;
+#pragma unroll
+        for (int k = 8; k < 17; k++) w32[k] = 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 17; k++) w32[k] = 0;
+        for (uint32_t k = 0; k < sbytes; k++) w32[k >> 2] |= (uint32_t)s[k] << (8 * (k & 3));
+    }
+    const uint32_t cmask = (1u << g.c) - 1, half = 1u << (g.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < g.W; w++) {
+        uint32_t bit = (uint32_t)w * g.c, wi = bit >> 5, sh = bit & 31;
+        uint64_t two = (uint64_t)w32[wi] | ((uint64_t)(wi + 1 < 17 ? w32[wi + 1] : 0) << 32);
+        uint32_t raw = ((uint32_t)(two >> sh) & cmask) + carry;
+        uint32_t key, val = (uint32_t)i;
+        if (raw > half) { raw = (1u << g.c) - raw; carry = 1; val |= 0x80000000u; } else carry = 0;
+        key = raw ? (uint32_t)w * g.B + raw - 1 : MSM_INVALID_KEY;
+        keys[(uint64_t)w * n + i] = key;
+        vals[(uint64_t)w * n + i] = val;
+    }
+}
+
+// number of valid (non-zero-digit) entries = first index whose sorted key is INVALID
+__global__ void k_count_valid(const uint32_t* __restrict__ keys, uint64_t total, uint64_t* __restrict__ out) {
+    if (blockIdx.x | threadIdx.x) return;
+    uint64_t lo = 0, hi = total;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (keys[mid] == MSM_INVALID_KEY) hi = mid; else lo = mid + 1; }
+    out[0] = lo;
+    // level sizes for the fold cascade: level 0 always emits ceil(M/SEG) heads; a level >= 1 with
+    // <= SEG inputs is the last one (single thread, everything folded into the buckets) and emits none.
+    uint64_t m = (lo + MSM_SEG - 1) / MSM_SEG;
+    out[1] = m;
+    for (int l = 2; l < 8; l++) { m = (m <= MSM_SEG) ? 0 : (m + MSM_SEG - 1) / MSM_SEG; out[l] = m; }
+}
+
+
+int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmGeom g, MsmScratch& scratch,
+                     cudaStream_t stream, MsmSorted* out, MsmLaunchStats* stats) {
+    const uint64_t total = n * (uint64_t)g.W;
+    const uint64_t nbuckets = (uint64_t)g.W * g.B;
+    if (sbytes == 0 || sbytes > 64) return (int)cudaErrorInvalidValue;
+    int key_bits = 1; while ((1ull << key_bits) < nbuckets) key_bits++;
+    int end_bit = key_bits + 1 > 32 ? 32 : key_bits + 1;   // INVALID (all ones) sorts after every valid key
+    size_t sort_tmp = 0;
+    cub::DoubleBuffer<uint32_t> kb(nullptr, nullptr), vb(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, kb, vb, (uint64_t)total, 0, end_bit, stream);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_keys0 = 0, o_keys1 = o_keys0 + al(total * 4), o_vals0 = o_keys1 + al(total * 4), o_vals1 = o_vals0 + al(total * 4);
+    size_t o_tmp = o_vals1 + al(total * 4), o_counts = o_tmp + al(sort_tmp);
+    uint8_t* base = (uint8_t*)scratch.get(o_counts + 256);
+    if (!base) return (int)cudaErrorMemoryAllocation;
+    uint32_t* keys0 = (uint32_t*)(base + o_keys0); uint32_t* keys1 = (uint32_t*)(base + o_keys1);
+    uint32_t* vals0 = (uint32_t*)(base + o_vals0); uint32_t* vals1 = (uint32_t*)(base + o_vals1);
+    uint64_t* counts = (uint64_t*)(base + o_counts);
+    int launches = 0;
+    k_digits<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_scalars, sbytes, n, g, keys0, vals0); launches++;
+    kb = cub::DoubleBuffer<uint32_t>(keys0, keys1); vb = cub::DoubleBuffer<uint32_t>(vals0, vals1);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, kb, vb, (uint64_t)total, 0, end_bit, stream);
+    if (e != cudaSuccess) return (int)e;
+    launches += 2 + (end_bit + 7) / 8;   // histogram + scan + one onesweep pass per 8 key bits
+    k_count_valid<<<1, 1, 0, stream>>>(kb.Current(), total, counts); launches++;
+    out->keys = kb.Current(); out->vals = vb.Current(); out->counts = counts; out->n = n; out->total = total; out->g = g;
+    if (stats) stats->launches += launches;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sb
