@@ -288,8 +288,8 @@ _Pragma("unroll")
     // inverse by Fermat (a^(p-2)); inverse of 0 is 0
     SB_HD static Fp inv(const Fp& a) {
         uint32_t e[N];
-        for (int i = 0; i < N; i++) e[i] = P::p(i);
-        e[0] -= 2;   // p is odd and p(0) >= 3 for all supported fields
+        uint32_t bw = 2;   // e = p - 2 with borrow propagation (BLS12-381 Fr has p(0) == 1)
+        for (int i = 0; i < N; i++) { uint32_t pi = P::p(i); e[i] = pi - bw; bw = pi < bw ? 1u : 0u; }
         return pow(a, e, N);
     }
 
