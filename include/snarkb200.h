@@ -91,6 +91,9 @@ int sb_groth16_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint6
 /* full file-to-proof convenience: reads the .wtns container, checks curve and length like the reference (:44-50). */
 int sb_groth16_prove_wtns(sb_ctx* ctx, uint64_t handle, const uint8_t* wtns, uint64_t wtns_len,
                           const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
+/* same proof with the witness uploaded by the previous sb_groth16_prove on this handle still resident in HBM
+ * (no host->device copy): the device-resident timing bench.py reports as `value`. */
+int sb_groth16_prove_resident(sb_ctx* ctx, uint64_t handle, const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
 int sb_groth16_release(sb_ctx* ctx, uint64_t handle);
 /* multi-GPU: this rank proves with its shard [shard, n_shards) of every MSM and returns the five un-normalised
  * MSM partials (A, B1, C, H in G1; B2 in G2) instead of a proof; the ranks exchange them (NCCL all-gather) and any
@@ -112,6 +115,15 @@ int sb_dev_download(sb_ctx* ctx, uint8_t* dst, const void* src_dev, uint64_t byt
 /* timing of the last call on this context, measured with CUDA events on the context's stream (ms):
  * which = 0 total device time of the call, 1.. = per-stage breakdown where the call defines one. */
 float sb_last_ms(sb_ctx* ctx, int which);
+/* counters of the last MSM / prove call: 0/1 = summed device time (ms) of the G1 / G2 bucket-accumulation kernel
+ * launches, 2/3 = number of those launches, 4/5 = (scalar digit, point) entries they consumed. */
+double sb_last_stat(sb_ctx* ctx, int which);
+/* integer-pipe calibration on this device: what = 0 -> IMAD.WIDE.U32 per second, 1 -> register-resident BN254 Fq
+ * Montgomery multiplies per second (the modmul-bound roofline denominators). */
+double sb_calibrate(sb_ctx* ctx, int what);
+/* synthetic bases for tests/benchmarks: P_i = (SplitMix64(seed+i)|1) * G, affine Montgomery, computed on the GPU. */
+int sb_gen_points(sb_ctx* ctx, int group, uint64_t seed, uint64_t n, uint8_t* out);
+int sb_generator(sb_ctx* ctx, int group, uint8_t* out_affine);
 int sb_sync(sb_ctx* ctx);
 
 #ifdef __cplusplus

@@ -45,6 +45,11 @@ _SIGNATURES = {
     "sb_groth16_prove": (ctypes.c_int, [vp, u64, vp, u64, vp, vp, vp]),
     "sb_groth16_prove_wtns": (ctypes.c_int, [vp, u64, vp, u64, vp, vp, vp]),
     "sb_groth16_release": (ctypes.c_int, [vp, u64]),
+    "sb_groth16_prove_resident": (ctypes.c_int, [vp, u64, vp, vp, vp]),
+    "sb_last_stat": (ctypes.c_double, [vp, ctypes.c_int]),
+    "sb_calibrate": (ctypes.c_double, [vp, ctypes.c_int]),
+    "sb_gen_points": (ctypes.c_int, [vp, ctypes.c_int, u64, u64, vp]),
+    "sb_generator": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "sb_groth16_prove_shard": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_int, ctypes.c_int, vp]),
     "sb_groth16_partials_bytes": (u32, [vp]),
     "sb_groth16_finish": (ctypes.c_int, [vp, u64, vp, ctypes.c_int, vp, vp, vp]),

@@ -15,6 +15,7 @@
 #include "fr_entry.h"
 
 using namespace sb;
+namespace sb { double calibrate(int what, cudaStream_t stream); }
 
 namespace {
 
@@ -36,10 +37,11 @@ struct GroupOps {
     void (*to_affine)(const uint8_t*, uint8_t*);
     void (*from_affine)(const uint8_t*, uint8_t*);
     void (*times)(const uint8_t*, const uint8_t*, int, uint8_t*);
+    int (*gen_points)(const uint8_t*, uint64_t, uint64_t, void*, cudaStream_t);
     uint32_t xyzz_bytes;
     uint32_t aff_bytes;
 };
-#define SB_GROUP_OPS(NAME, AFF) GroupOps{NAME##_buckets, NAME##_combine, NAME##_add, NAME##_to_jacobian, NAME##_to_affine, NAME##_from_affine, NAME##_times, NAME##_xyzz_bytes(), AFF}
+#define SB_GROUP_OPS(NAME, AFF) GroupOps{NAME##_buckets, NAME##_combine, NAME##_add, NAME##_to_jacobian, NAME##_to_affine, NAME##_from_affine, NAME##_times, NAME##_gen_points, NAME##_xyzz_bytes(), AFF}
 
 struct NttTab { DevBuf lo, hi; int h = 0; };
 struct PreTab { DevBuf lo, hi; int h = 0; std::string key; };
@@ -78,6 +80,9 @@ struct sb_ctx {
     int fr_s = 0;
     std::vector<std::vector<uint8_t>> roots;   // w[0..s] Montgomery bytes
     std::vector<uint8_t> nqr, shift;
+    std::vector<uint8_t> gen1, gen2;            // affine generators, Montgomery
+    cudaEvent_t prof_ev[64];
+    double stat[8] = {0};                        // see sb_last_stat
 };
 
 namespace {
@@ -214,6 +219,47 @@ int get_pre(sb_ctx* c, uint64_t n, const uint8_t* first, const uint8_t* inc, FrP
     return 0;
 }
 
+// affine generators as plain big-endian hex (build/snarkjs.js:9468-9472, 9419-9422 region; 10821-10833 for BLS12-381)
+template <class P> void hex_to_mont(const char* hex, uint8_t* out) {
+    typedef Fp<P> F; F a = F::zero();
+    int len = (int)strlen(hex);
+    for (int i = 0; i < len; i++) {
+        char ch = hex[len - 1 - i];
+        uint32_t d = (ch >= '0' && ch <= '9') ? ch - '0' : (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : ch - 'A' + 10;
+        a.v[i / 8] |= d << (4 * (i % 8));
+    }
+    a = F::to_mont(a); memcpy(out, &a, sizeof a);
+}
+void init_generators(sb_ctx* c) {
+    if (c->curve == SB_BN254) {
+        c->gen1.resize(64); c->gen2.resize(128);
+        hex_to_mont<BnFq>("1", c->gen1.data()); hex_to_mont<BnFq>("2", c->gen1.data() + 32);
+        hex_to_mont<BnFq>("1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed", c->gen2.data());
+        hex_to_mont<BnFq>("198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2", c->gen2.data() + 32);
+        hex_to_mont<BnFq>("12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa", c->gen2.data() + 64);
+        hex_to_mont<BnFq>("090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b", c->gen2.data() + 96);
+    } else {
+        c->gen1.resize(96); c->gen2.resize(192);
+        hex_to_mont<BlsFq>("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb", c->gen1.data());
+        hex_to_mont<BlsFq>("08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1", c->gen1.data() + 48);
+        hex_to_mont<BlsFq>("024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8", c->gen2.data());
+        hex_to_mont<BlsFq>("13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e", c->gen2.data() + 48);
+        hex_to_mont<BlsFq>("0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801", c->gen2.data() + 96);
+        hex_to_mont<BlsFq>("0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be", c->gen2.data() + 144);
+    }
+}
+
+// profiling helpers: accumulate-kernel event pairs
+void prof_begin(sb_ctx* c) { c->stats.ev = c->prof_ev; c->stats.nev = 64; c->stats.used = 0; for (double& d : c->stat) d = 0; }
+void prof_end(sb_ctx* c) {
+    for (int i = 0; i + 1 < c->stats.used; i += 2) {
+        float ms = 0; cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]);
+        int g = c->stats.tag[i / 2];
+        if (g == SB_G1) { c->stat[0] += ms; c->stat[2] += 1; } else { c->stat[1] += ms; c->stat[3] += 1; }
+    }
+    c->stats.ev = nullptr; c->stats.used = 0;
+}
+
 void tick(sb_ctx* c, int i) { cudaEventRecord(c->ev[i], c->stream); }
 float elapsed(sb_ctx* c, int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; }
 
@@ -232,11 +278,15 @@ int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const 
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
         void* d_wsum = c->io[3].get((size_t)g.W * G.xyzz_bytes);
         if (!d_wsum) return fail(c, SB_ERR_NOMEM, "out of device memory");
+        c->stats.cur_tag = (&G == &c->g1) ? SB_G1 : SB_G2;
         rc = G.buckets((const uint8_t*)d_bases + off * G.aff_bytes, s, c->bucket_scratch, c->stream, d_wsum, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
         std::vector<uint8_t> ws((size_t)g.W * G.xyzz_bytes);
+        uint64_t entries = 0;
         CU(c, cudaMemcpyAsync(ws.data(), d_wsum, ws.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(&entries, s.counts, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
+        c->stat[(&G == &c->g1) ? 4 : 5] += (double)entries;
         G.combine(ws.data(), g, acc_xyzz);
     }
     return 0;
@@ -262,10 +312,12 @@ int msm_host_inputs(sb_ctx* c, int group, const uint8_t* bases, const void* d_ba
         if (!d_sc) return fail(c, SB_ERR_NOMEM, "out of device memory");
         CU(c, cudaMemcpyAsync(d_sc, scalars, n * sbytes, cudaMemcpyHostToDevice, c->stream));
         tick(c, 1);
+        prof_begin(c);
         int rc = msm_dev_accumulate(c, G, d_bases, d_sc, sbytes, n, acc.data());
         if (rc) return rc;
         tick(c, 2);
         cudaEventSynchronize(c->ev[2]);
+        prof_end(c);
         c->last_ms[0] = elapsed(c, 0, 2); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2);
     }
     if (out_partial) memcpy(out_partial, acc.data(), acc.size());
@@ -331,6 +383,8 @@ int sb_create(int curve, int device_id, sb_ctx** out) {
     else { c->g1 = SB_GROUP_OPS(bls12381_g1, 96); c->g2 = SB_GROUP_OPS(bls12381_g2, 192); }
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return SB_ERR_CUDA; }
     for (auto& e : c->ev) cudaEventCreate(&e);
+    for (auto& e : c->prof_ev) cudaEventCreate(&e);
+    init_generators(c);
     int rc = curve == SB_BN254 ? init_roots<BnFr>(c) : init_roots<BlsFr>(c);
     if (rc == 0 && fr_configure(curve) != 0) rc = SB_ERR_CUDA;
     if (rc) { sb_destroy(c); return rc; }
@@ -352,6 +406,7 @@ void sb_destroy(sb_ctx* c) {
     for (auto& b : c->io) b.release();
     c->sort_scratch.release(); c->bucket_scratch.release();
     for (auto& e : c->ev) cudaEventDestroy(e);
+    for (auto& e : c->prof_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -414,8 +469,10 @@ int sb_msm_dev(sb_ctx* c, int group, const void* bases_dev, const void* scalars_
     const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
     std::vector<uint8_t> acc(G.xyzz_bytes, 0);
     tick(c, 0);
+    prof_begin(c);
     if (n) { int rc = msm_dev_accumulate(c, G, bases_dev, (const uint8_t*)scalars_dev, sb, n, acc.data()); if (rc) return rc; }
     tick(c, 1); cudaEventSynchronize(c->ev[1]); c->last_ms[0] = elapsed(c, 0, 1);
+    prof_end(c);
     G.to_jacobian(acc.data(), out);
     return 0;
 }
@@ -519,6 +576,26 @@ int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) {
     else if (what >= 0 && what <= c->fr_s) memcpy(out, c->roots[what].data(), 32);
     else return fail(c, SB_ERR_ARG, "root index out of range");
     return c->fr_s;
+}
+
+double sb_last_stat(sb_ctx* c, int which) { return (c && which >= 0 && which < 8) ? c->stat[which] : 0.0; }
+double sb_calibrate(sb_ctx* c, int what) { if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
+int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out) {
+    if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
+    const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
+    void* d = c->io[0].get(n * G.aff_bytes);
+    if (!d) return fail(c, SB_ERR_NOMEM, "out of device memory");
+    int rc = G.gen_points(group == SB_G1 ? c->gen1.data() : c->gen2.data(), seed, n, d, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "gen_points");
+    CU(c, cudaMemcpyAsync(out, d, n * G.aff_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sb_generator(sb_ctx* c, int group, uint8_t* out) {
+    if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
+    const std::vector<uint8_t>& g = group == SB_G1 ? c->gen1 : c->gen2;
+    memcpy(out, g.data(), g.size()); return 0;
 }
 
 void* sb_dev_alloc(sb_ctx* c, uint64_t bytes) { if (!c) return nullptr; cudaSetDevice(c->device); void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; return p; }
@@ -631,14 +708,15 @@ uint32_t sb_groth16_partials_bytes(sb_ctx* c) { return c ? 4 * c->g1.xyzz_bytes 
 
 // device part of the prover: returns the five MSM partials (A, B1, C, H | B2) as host XYZZ bytes.
 static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials) {
-    if (n_witness != k->nVars) return fail(c, SB_ERR_ARG, "Invalid witness length. Circuit: " + std::to_string(k->nVars) + ", witness: " + std::to_string(n_witness));
+    if (witness && n_witness != k->nVars) return fail(c, SB_ERR_ARG, "Invalid witness length. Circuit: " + std::to_string(k->nVars) + ", witness: " + std::to_string(n_witness));
     cudaSetDevice(c->device);
     const uint64_t n = k->domainSize, nv = k->nVars;
     const int cv = c->curve;
     int rc;
     tick(c, 0);
-    CU(c, cudaMemcpyAsync(k->dW, witness, nv * 32, cudaMemcpyHostToDevice, c->stream));
+    if (witness) CU(c, cudaMemcpyAsync(k->dW, witness, nv * 32, cudaMemcpyHostToDevice, c->stream));
     tick(c, 1);
+    prof_begin(c);
     // buildABC1 (:147-187)
     rc = fr_qap_rows(cv, k->d_rowptr, k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, n, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_qap_rows");
@@ -677,13 +755,18 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         uint8_t* ws = (uint8_t*)k->dWsum;
         size_t w1 = (size_t)g.W * G1.xyzz_bytes, w2 = (size_t)g.W * G2.xyzz_bytes;
         if (3 * w1 + w2 > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
+        c->stats.cur_tag = SB_G1;
         rc = G1.buckets((const uint8_t*)k->dA + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm A");
         rc = G1.buckets((const uint8_t*)k->dB1 + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B1");
         rc = G1.buckets((const uint8_t*)k->dC + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + 2 * w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm C");
+        c->stats.cur_tag = SB_G2;
         rc = G2.buckets((const uint8_t*)k->dB2 + base * G2.aff_bytes, s, c->bucket_scratch, c->stream, ws + 3 * w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B2");
         std::vector<uint8_t> hw(3 * w1 + w2);
+        uint64_t entries = 0;
         CU(c, cudaMemcpyAsync(hw.data(), ws, hw.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(&entries, s.counts, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
+        c->stat[4] += 3.0 * (double)entries; c->stat[5] += (double)entries;
         G1.combine(hw.data(), g, pA); G1.combine(hw.data() + w1, g, pB1); G1.combine(hw.data() + 2 * w1, g, pC); G2.combine(hw.data() + 3 * w1, g, pB2);
     }
     tick(c, 3);
@@ -694,6 +777,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     }
     tick(c, 4);
     cudaEventSynchronize(c->ev[4]);
+    prof_end(c);
     c->last_ms[0] = elapsed(c, 0, 4); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2); c->last_ms[3] = elapsed(c, 2, 3); c->last_ms[4] = elapsed(c, 3, 4);
     return 0;
 }
@@ -734,6 +818,12 @@ int sb_groth16_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_w
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
     int rc = groth16_device(c, k, witness, n_witness, 0, 1, partials.data()); if (rc) return rc;
+    return groth16_assemble(c, k, partials.data(), r, s, proof);
+}
+int sb_groth16_prove_resident(sb_ctx* c, uint64_t h, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
+    int rc = groth16_device(c, k, nullptr, k->nVars, 0, 1, partials.data()); if (rc) return rc;
     return groth16_assemble(c, k, partials.data(), r, s, proof);
 }
 int sb_groth16_prove_shard(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials_out) {

@@ -188,6 +188,30 @@ k_window_sum(const XYZZ<F>* __restrict__ partials, uint32_t per_window, XYZZ<F>*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Synthetic bases for benchmarks and tests: P_i = k_i * G with k_i = SplitMix64(seed + i) (64-bit), written
+// as affine Montgomery points.  One thread per point: double-and-add in XYZZ, then one field inversion.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_gen_points(Affine<F> g, uint64_t seed, uint64_t n, Affine<F>* __restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = splitmix64(seed + i) | 1ull;
+    const F one = F::one();
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int bit = 63; bit >= 0; bit--) {
+        r = XYZZ<F>::dbl(r);
+        if ((k >> bit) & 1) r.add_affine(g.x, g.y, one);
+    }
+    Affine<F> a;
+    if (r.is_inf()) { a.x = F::zero(); a.y = F::zero(); }
+    else { F t = F::inv(F::mul(r.zz, r.zzz)); a.x = F::mul(r.x, F::mul(t, r.zzz)); a.y = F::mul(r.y, F::mul(t, r.zz)); }
+    store_vec(out + i, a);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Device scratch (grow-only) and the two halves of the pipeline.
 // ------------------------------------------------------------------------------------------------
 struct MsmScratch {
@@ -199,7 +223,11 @@ struct MsmScratch {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct MsmLaunchStats { int launches = 0; };
+struct MsmLaunchStats {
+    int launches = 0;
+    // optional profiling: event pairs recorded around each k_accumulate launch (tag = group id)
+    cudaEvent_t* ev = nullptr; int nev = 0; int used = 0; int tag[32] = {0}; int cur_tag = 0;
+};
 
 // Sorted digit entries of one scalar vector; shared by every MSM that uses the same scalars
 // (Groth16: A, B1, B2 and C all multiply the witness, src/groth16_prove.js:84-97).
@@ -239,8 +267,11 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     int launches = 0;
     cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), stream);
     if (heads0) {
+        const bool prof = stats && stats->ev && stats->used + 2 <= stats->nev && stats->used / 2 < 32;
+        if (prof) cudaEventRecord(stats->ev[stats->used], stream);
         k_accumulate<F><<<(unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
             d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); launches++;
+        if (prof) { cudaEventRecord(stats->ev[stats->used + 1], stream); stats->tag[stats->used / 2] = stats->cur_tag; stats->used += 2; }
         // fold cascade: level l consumes counts[l] heads (upper bound m on the host, exact count on the device)
         uint64_t m = heads0; int level = 1;
         XYZZ<F>* hin = headsA; uint32_t* kin = hkA; XYZZ<F>* hout = headsB; uint32_t* kout = hkB;

@@ -35,5 +35,10 @@ void bls12381_g1_times(const uint8_t* xyzz, const uint8_t* k, int nbytes, uint8_
     for (int i = nbytes * 8 - 1; i >= 0; i--) { r = PT::dbl(r); if ((k[i >> 3] >> (i & 7)) & 1) r.add(p); }
     memcpy(out, &r, sizeof r);
 }
+int bls12381_g1_gen_points(const uint8_t* gen_affine, uint64_t seed, uint64_t n, void* d_out, cudaStream_t stream) {
+    Affine<FT> g; memcpy(&g, gen_affine, sizeof g);
+    if (n) k_gen_points<FT><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g, seed, n, (Affine<FT>*)d_out);
+    return (int)cudaGetLastError();
+}
 uint32_t bls12381_g1_xyzz_bytes() { return (uint32_t)sizeof(PT); }
 }

@@ -271,3 +271,44 @@ def test_groth16_errors(bn, golden):
     with pytest.raises(SbError, match="Invalid File format"):
         groth16.ProvingKey(b"nope" + zkey[4:], curve=bn)
     pk.release()
+
+
+# ----------------------------------------------------------------------------------------------- synthetic workloads
+def _splitmix(x):
+    M = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & M
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+    return x ^ (x >> 31)
+
+
+@pytest.mark.parametrize("cname,cid", [("bn128", BN), ("bls12381", BLS)])
+def test_gen_points_are_k_times_generator(bn, bls, cname, cid):
+    from snarkjs_b200 import synth
+    c = bn if cid == BN else bls
+    ci = O.CURVES[cid]
+    for grp in (1, 2):
+        pts = synth.gen_points(c, grp, 42, 9).tobytes()
+        sz = ci.n8q * 2 * grp
+        gen = ci.g1_affine_bytes(ci.g1) if grp == 1 else ci.g2_affine_bytes(ci.g2)
+        gj = O.g_from_affine(cid, grp, gen)
+        for i in (0, 3, 8):
+            k = _splitmix(42 + i) | 1
+            want = O.g_to_affine(cid, grp, O.g_times(cid, grp, gj, k.to_bytes(8, "little")))
+            assert pts[i * sz:(i + 1) * sz] == want, (cname, grp, i)
+
+
+def test_groth16_synthetic_2_16_matches_oracle(bn):
+    """Synthetic chain circuit at 2^16 (unstructured key): fused GPU proof == oracle proof, byte for byte."""
+    from snarkjs_b200 import groth16, synth
+    L = 16
+    zkey = synth.synth_groth16_zkey(bn, L, seed=3)
+    w = synth.chain_witness(bn.r, L)
+    wt = synth.wtns_container(bn.r, w)
+    ci = O.CURVES[BN]
+    r, s = ci.fr_to_mont(99), ci.fr_to_mont(77)
+    pk = groth16.ProvingKey(zkey, curve=bn)
+    proof, pub = groth16.prove(pk, wt, r, s)
+    oproof, opub = O.groth16_prove(zkey, wt, r, s)
+    assert proof == oproof and pub == [str(x) for x in opub]
+    pk.release()
