@@ -121,6 +121,8 @@ double sb_last_stat(sb_ctx* ctx, int which);
 /* integer-pipe calibration on this device: what = 0 -> IMAD.WIDE.U32 per second, 1 -> register-resident BN254 Fq
  * Montgomery multiplies per second (the modmul-bound roofline denominators). */
 double sb_calibrate(sb_ctx* ctx, int what);
+/* experimental kernel-variant selection (process-wide): key 0 = bucket-accumulation minBlocksPerSM variant. */
+int sb_set_tuning(int key, int value);
 /* synthetic bases for tests/benchmarks: P_i = (SplitMix64(seed+i)|1) * G, affine Montgomery, computed on the GPU. */
 int sb_gen_points(sb_ctx* ctx, int group, uint64_t seed, uint64_t n, uint8_t* out);
 int sb_generator(sb_ctx* ctx, int group, uint8_t* out_affine);

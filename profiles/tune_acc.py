@@ -1,0 +1,25 @@
+"""Times the bucket-accumulation kernel variants (sb_set_tuning) on a 2^20 G1 / G2 MSM + calibration."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import snarkjs_b200
+from snarkjs_b200 import synth
+from snarkjs_b200.curve import _ptr
+c = snarkjs_b200.getCurveFromName("bn128")
+lib, h = c.lib, c.handle
+print("calib imad.wide/s %.3e  modmul/s %.3e" % (lib.sb_calibrate(h, 0), lib.sb_calibrate(h, 1)))
+n = 1 << 20
+rng = np.random.default_rng(1)
+sc = rng.integers(0, 256, size=n * 32, dtype=np.uint8); sc.reshape(n, 32)[:, 31] &= 0x1f
+for grp in (1, 2):
+    bases = synth.gen_points(c, grp, 7, n)
+    hb = (c.G1 if grp == 1 else c.G2).registerBases(bases)
+    ref = None
+    for v in (4, 5, 6, 8, 4):
+        lib.sb_set_tuning(0, v)
+        G = c.G1 if grp == 1 else c.G2
+        for _ in range(3):
+            out = G.multiExpRegistered(hb, sc)
+        if ref is None: ref = out.tobytes()
+        assert out.tobytes() == ref
+        print(f"G{grp} variant {v}: acc kernel {lib.sb_last_stat(h, grp - 1):.3f} ms, msm total {c.last_ms(0):.3f} ms (h2d {c.last_ms(1):.3f})")

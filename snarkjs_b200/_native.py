@@ -48,6 +48,7 @@ _SIGNATURES = {
     "sb_groth16_prove_resident": (ctypes.c_int, [vp, u64, vp, vp, vp]),
     "sb_last_stat": (ctypes.c_double, [vp, ctypes.c_int]),
     "sb_calibrate": (ctypes.c_double, [vp, ctypes.c_int]),
+    "sb_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "sb_gen_points": (ctypes.c_int, [vp, ctypes.c_int, u64, u64, vp]),
     "sb_generator": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "sb_groth16_prove_shard": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_int, ctypes.c_int, vp]),

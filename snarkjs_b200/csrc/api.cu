@@ -38,20 +38,23 @@ struct GroupOps {
     void (*from_affine)(const uint8_t*, uint8_t*);
     void (*times)(const uint8_t*, const uint8_t*, int, uint8_t*);
     int (*gen_points)(const uint8_t*, uint64_t, uint64_t, void*, cudaStream_t);
+    int (*precompute)(const void*, uint64_t, int, int, void*, cudaStream_t);
     uint32_t xyzz_bytes;
     uint32_t aff_bytes;
 };
-#define SB_GROUP_OPS(NAME, AFF) GroupOps{NAME##_buckets, NAME##_combine, NAME##_add, NAME##_to_jacobian, NAME##_to_affine, NAME##_from_affine, NAME##_times, NAME##_gen_points, NAME##_xyzz_bytes(), AFF}
+#define SB_GROUP_OPS(NAME, AFF) GroupOps{NAME##_buckets, NAME##_combine, NAME##_add, NAME##_to_jacobian, NAME##_to_affine, NAME##_from_affine, NAME##_times, NAME##_gen_points, NAME##_precompute, NAME##_xyzz_bytes(), AFF}
 
 struct NttTab { DevBuf lo, hi; int h = 0; };
 struct PreTab { DevBuf lo, hi; int h = 0; std::string key; };
 
-struct BaseSet { int group = 0; uint64_t n = 0; void* d = nullptr; };
+struct BaseSet { int group = 0; uint64_t n = 0; void* d = nullptr; void* table = nullptr; MsmGeom gp{}; };
 
 struct Groth16Key {
     uint32_t nVars = 0, nPublic = 0, domainSize = 0; int power = 0;
     std::vector<uint8_t> alpha1, beta1, beta2, gamma2, delta1, delta2;
     void *dA = nullptr, *dB1 = nullptr, *dB2 = nullptr, *dC = nullptr, *dH = nullptr;   // bases (C padded to nVars)
+    void *tA = nullptr, *tB1 = nullptr, *tB2 = nullptr, *tC = nullptr, *tH = nullptr;   // precomputed window tables
+    MsmGeom gpW{}, gpH{};                                                                // their geometry (precomp != 0 when built)
     uint64_t* d_rowptr = nullptr; uint32_t* d_sig = nullptr; void* d_coef = nullptr; uint64_t nCoef = 0;
     // device work buffers
     void *dW = nullptr, *dA_T = nullptr, *dB_T = nullptr, *dC_T = nullptr, *dTmp = nullptr, *dWsum = nullptr;
@@ -66,6 +69,10 @@ struct sb_ctx {
     uint32_t n8q = 32;
     GroupOps g1, g2;
     MsmScratch sort_scratch, bucket_scratch;
+    MsmScratch sort_scratch2, bscr[5];           // per-MSM scratch for the overlapped Groth16 pipeline
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pev[16];                         // pipeline events
+    uint8_t* pinned = nullptr;                   // 256 KiB pinned staging (window sums, counters)
     MsmLaunchStats stats;
     uint64_t launches = 0;
     DevBuf io[4];
@@ -260,6 +267,25 @@ void prof_end(sb_ctx* c) {
     c->stats.ev = nullptr; c->stats.used = 0;
 }
 
+// Precomputed window tables (msm.cuh k_precompute).  Built for sets of >= 2^12 points whose table index fits the
+// 31-bit entry value; g_msm_tuning[3] != 0 disables them (plain windowed Pippenger on the raw bases).
+bool want_precomp(uint64_t n) {
+    if (g_msm_tuning[3] != 0 || n < (1ull << 12)) return false;
+    MsmGeom g = msm_geometry_precomp(n, 32);
+    return (uint64_t)g.W * n < (1ull << 31);
+}
+int build_table(sb_ctx* c, const GroupOps& G, const void* d_bases, uint64_t n, void** table, MsmGeom* gp) {
+    MsmGeom g = msm_geometry_precomp(n, 32);
+    cudaError_t e = cudaMalloc(table, (size_t)g.W * n * G.aff_bytes);
+    if (e != cudaSuccess) { *table = nullptr; return cuda_fail(c, e, "precompute table allocation"); }
+    int rc = G.precompute(d_bases, n, g.c, g.W, *table, c->stream); c->launches++;
+    if (rc) return cuda_fail(c, (cudaError_t)rc, "k_precompute");
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "k_precompute");
+    *gp = g;
+    return 0;
+}
+
 void tick(sb_ctx* c, int i) { cudaEventRecord(c->ev[i], c->stream); }
 float elapsed(sb_ctx* c, int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; }
 
@@ -268,20 +294,23 @@ float elapsed(sb_ctx* c, int a, int b) { float ms = 0; cudaEventElapsedTime(&ms,
 // acc (host XYZZ bytes) += result
 // ------------------------------------------------------------------------------------------------------------
 int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const uint8_t* d_scalars, uint32_t sbytes, uint64_t n,
-                       uint8_t* acc_xyzz) {
+                       uint8_t* acc_xyzz, const MsmGeom* gp = nullptr, uint64_t first = 0) {
     static const uint64_t MAXC = 1ull << 23;
     for (uint64_t off = 0; off < n; off += MAXC) {
         uint64_t cn = std::min(MAXC, n - off);
         MsmGeom g = msm_geometry(cn, sbytes);
+        if (gp) {   // registered set with precomputed window multiples: d_bases is the table
+            g = *gp; g.first = first + off; g.W = (int)((8 * sbytes + 1 + g.c - 1) / g.c);
+        }
         MsmSorted s;
         int rc = msm_sort_entries(d_scalars + off * sbytes, sbytes, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
-        void* d_wsum = c->io[3].get((size_t)g.W * G.xyzz_bytes);
+        void* d_wsum = c->io[3].get((size_t)g.windows() * G.xyzz_bytes);
         if (!d_wsum) return fail(c, SB_ERR_NOMEM, "out of device memory");
         c->stats.cur_tag = (&G == &c->g1) ? SB_G1 : SB_G2;
-        rc = G.buckets((const uint8_t*)d_bases + off * G.aff_bytes, s, c->bucket_scratch, c->stream, d_wsum, &c->stats);
+        rc = G.buckets(gp ? d_bases : (const void*)((const uint8_t*)d_bases + off * G.aff_bytes), s, c->bucket_scratch, c->stream, d_wsum, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
-        std::vector<uint8_t> ws((size_t)g.W * G.xyzz_bytes);
+        std::vector<uint8_t> ws((size_t)g.windows() * G.xyzz_bytes);
         uint64_t entries = 0;
         CU(c, cudaMemcpyAsync(ws.data(), d_wsum, ws.size(), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(&entries, s.counts, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -293,7 +322,7 @@ int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const 
 }
 
 int msm_host_inputs(sb_ctx* c, int group, const uint8_t* bases, const void* d_bases_opt, const uint8_t* scalars, uint32_t sbytes,
-                    uint64_t n, uint8_t* out_jac, uint8_t* out_partial) {
+                    uint64_t n, uint8_t* out_jac, uint8_t* out_partial, const MsmGeom* gp = nullptr, uint64_t first = 0) {
     if (!c) return SB_ERR_ARG;
     const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
     std::vector<uint8_t> acc(G.xyzz_bytes, 0);
@@ -313,7 +342,7 @@ int msm_host_inputs(sb_ctx* c, int group, const uint8_t* bases, const void* d_ba
         CU(c, cudaMemcpyAsync(d_sc, scalars, n * sbytes, cudaMemcpyHostToDevice, c->stream));
         tick(c, 1);
         prof_begin(c);
-        int rc = msm_dev_accumulate(c, G, d_bases, d_sc, sbytes, n, acc.data());
+        int rc = msm_dev_accumulate(c, G, d_bases, d_sc, sbytes, n, acc.data(), gp, first);
         if (rc) return rc;
         tick(c, 2);
         cudaEventSynchronize(c->ev[2]);
@@ -355,7 +384,7 @@ bool modulus_matches(const uint8_t* p, uint32_t n8, int curve, bool scalar_field
 }
 
 void free_key(Groth16Key* k) {
-    for (void* p : {k->dA, k->dB1, k->dB2, k->dC, k->dH, (void*)k->d_rowptr, (void*)k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, k->dTmp, k->dWsum})
+    for (void* p : {k->tA, k->tB1, k->tB2, k->tC, k->tH, k->dA, k->dB1, k->dB2, k->dC, k->dH, (void*)k->d_rowptr, (void*)k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, k->dTmp, k->dWsum})
         if (p) cudaFree(p);
     delete k;
 }
@@ -384,6 +413,9 @@ int sb_create(int curve, int device_id, sb_ctx** out) {
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return SB_ERR_CUDA; }
     for (auto& e : c->ev) cudaEventCreate(&e);
     for (auto& e : c->prof_ev) cudaEventCreate(&e);
+    for (auto& e : c->pev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& st : c->aux) cudaStreamCreate(&st);
+    if (cudaHostAlloc((void**)&c->pinned, 256 * 1024, cudaHostAllocDefault) != cudaSuccess) c->pinned = nullptr;
     init_generators(c);
     int rc = curve == SB_BN254 ? init_roots<BnFr>(c) : init_roots<BlsFr>(c);
     if (rc == 0 && fr_configure(curve) != 0) rc = SB_ERR_CUDA;
@@ -397,7 +429,7 @@ void sb_destroy(sb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto* k : c->keys) if (k) free_key(k);
-    for (auto& b : c->bases) if (b.d) cudaFree(b.d);
+    for (auto& b : c->bases) { if (b.d) cudaFree(b.d); if (b.table) cudaFree(b.table); }
     for (auto* t : c->pre_cache) { t->lo.release(); t->hi.release(); delete t; }
     for (auto& kv : c->ntt_fwd) { kv.second.lo.release(); kv.second.hi.release(); }
     for (auto& kv : c->ntt_inv) { kv.second.lo.release(); kv.second.hi.release(); }
@@ -407,6 +439,10 @@ void sb_destroy(sb_ctx* c) {
     c->sort_scratch.release(); c->bucket_scratch.release();
     for (auto& e : c->ev) cudaEventDestroy(e);
     for (auto& e : c->prof_ev) cudaEventDestroy(e);
+    for (auto& e : c->pev) cudaEventDestroy(e);
+    for (auto& st : c->aux) { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } }
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->sort_scratch2.release(); for (auto& b : c->bscr) b.release();
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -430,6 +466,7 @@ int sb_bases_register(sb_ctx* c, int group, const uint8_t* bases, uint64_t n, ui
     BaseSet b; b.group = group; b.n = n;
     CU(c, cudaMalloc(&b.d, n ? n * G.aff_bytes : 16));
     CU(c, cudaMemcpy(b.d, bases, n * G.aff_bytes, cudaMemcpyHostToDevice));
+    if (want_precomp(n)) { int rc = build_table(c, G, b.d, n, &b.table, &b.gp); if (rc) { cudaFree(b.d); return rc; } }
     c->bases.push_back(b);
     *handle = c->bases.size();
     return 0;
@@ -438,6 +475,7 @@ int sb_bases_release(sb_ctx* c, uint64_t h) {
     if (!c || h == 0 || h > c->bases.size() || !c->bases[h - 1].d) return fail(c, SB_ERR_ARG, "invalid bases handle");
     cudaSetDevice(c->device);
     cudaFree(c->bases[h - 1].d); c->bases[h - 1].d = nullptr; c->bases[h - 1].n = 0;
+    if (c->bases[h - 1].table) { cudaFree(c->bases[h - 1].table); c->bases[h - 1].table = nullptr; }
     return 0;
 }
 static int msm_registered_impl(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out, uint8_t* partial) {
@@ -445,6 +483,8 @@ static int msm_registered_impl(sb_ctx* c, uint64_t h, uint64_t first, const uint
     const BaseSet& b = c->bases[h - 1];
     if (first + n > b.n) return fail(c, SB_ERR_ARG, "registered base range out of bounds");
     const GroupOps& G = b.group == SB_G1 ? c->g1 : c->g2;
+    if (b.table && sb >= 1 && sb <= 32)
+        return msm_host_inputs(c, b.group, nullptr, b.table, scalars, sb, n, out, partial, &b.gp, first);
     return msm_host_inputs(c, b.group, nullptr, (const uint8_t*)b.d + first * G.aff_bytes, scalars, sb, n, out, partial);
 }
 int sb_msm_registered(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
@@ -578,6 +618,7 @@ int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) {
     return c->fr_s;
 }
 
+int sb_set_tuning(int key, int value) { if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0; }
 double sb_last_stat(sb_ctx* c, int which) { return (c && which >= 0 && which < 8) ? c->stat[which] : 0.0; }
 double sb_calibrate(sb_ctx* c, int what) { if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
 int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out) {
@@ -677,6 +718,14 @@ int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle
     up(&k->dA_T, nullptr, 0, n * 32); up(&k->dB_T, nullptr, 0, n * 32); up(&k->dC_T, nullptr, 0, n * 32); up(&k->dTmp, nullptr, 0, n * 32);
     up(&k->dWsum, nullptr, 0, 8 * 80 * 4 * 96);
     if (e != cudaSuccess) { free_key(k); return cuda_fail(c, e, "sb_groth16_load upload"); }
+    if (want_precomp(nv) && want_precomp(n)) {
+        int rc2 = build_table(c, c->g1, k->dA, nv, &k->tA, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g1, k->dB1, nv, &k->tB1, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g2, k->dB2, nv, &k->tB2, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g1, k->dC, nv, &k->tC, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g1, k->dH, n, &k->tH, &k->gpH);
+        if (rc2) { free_key(k); return rc2; }
+    }
     c->keys.push_back(k);
     *handle = c->keys.size();
     return 0;
@@ -717,6 +766,8 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     if (witness) CU(c, cudaMemcpyAsync(k->dW, witness, nv * 32, cudaMemcpyHostToDevice, c->stream));
     tick(c, 1);
     prof_begin(c);
+    void* tmp = k->dTmp;
+    auto run_qap_ntt = [&]() -> int {
     // buildABC1 (:147-187)
     rc = fr_qap_rows(cv, k->d_rowptr, k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, n, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_qap_rows");
@@ -726,7 +777,6 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     if (cv == SB_BN254) ninv_bytes<BnFr>(k->power, ninv); else ninv_bytes<BlsFr>(k->power, ninv);
     FrPre pre; rc = get_pre(c, n, ninv, inc, &pre); if (rc) return rc;
     void* odd[3]; void* bufs[3] = {k->dA_T, k->dB_T, k->dC_T};
-    void* tmp = k->dTmp;
     for (int i = 0; i < 3; i++) {
         void* r1 = nullptr; void* r2 = nullptr;
         rc = ntt_dev(c, bufs[i], tmp, n, 1, nullptr, false, &r1); if (rc) return rc;
@@ -738,7 +788,8 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     // joinABC (:320-374) -> plain scalars for the H MSM, written over the remaining scratch buffer
     rc = fr_join_abc(cv, odd[0], odd[1], odd[2], tmp, n, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_join_abc");
-    tick(c, 2);
+    return 0;
+    };
     // MSMs (:84-101).  Shard = contiguous point range; shard 0 of 1 = everything.
     auto range = [&](uint64_t total, uint64_t& lo, uint64_t& cnt) { uint64_t per = (total + n_shards - 1) / n_shards; lo = std::min(total, per * shard); cnt = std::min(total - lo, per); };
     const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
@@ -746,6 +797,69 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     memset(partials, 0, 4 * G1.xyzz_bytes + G2.xyzz_bytes);
     static const uint64_t MAXC = 1ull << 23;
     uint64_t wlo, wcnt; range(nv, wlo, wcnt);
+    uint64_t hlo, hcnt; range(n, hlo, hcnt);
+    if (wcnt <= MAXC && hcnt <= MAXC && wcnt > 0 && hcnt > 0 && c->pinned) {
+        // Overlapped pipeline: the witness is sorted once (A, B1, B2 and C all multiply it, :84-97); the four bucket
+        // pipelines run on their own streams so that the latency-bound tails (fold cascade, bucket reduction) of one
+        // MSM hide under the throughput-bound accumulation of the next; the H scalars (QAP/NTT chain) are produced
+        // concurrently on the main stream.  g_msm_tuning[2] != 0 serialises everything on one stream (profiling).
+        const bool serial = g_msm_tuning[2] != 0;
+        cudaStream_t s0 = c->stream;
+        cudaStream_t sx[4] = {serial ? s0 : c->aux[0], serial ? s0 : c->aux[1], serial ? s0 : c->aux[2], serial ? s0 : c->aux[3]};
+        MsmGeom gw = msm_geometry(wcnt, 32), gh = msm_geometry(hcnt, 32);
+        const bool pre = k->tA != nullptr;
+        if (pre) { gw = k->gpW; gw.first = wlo; gh = k->gpH; gh.first = hlo; }
+        const size_t w1 = (size_t)gw.windows() * G1.xyzz_bytes, w2 = (size_t)gw.windows() * G2.xyzz_bytes, wh = (size_t)gh.windows() * G1.xyzz_bytes;
+        if (3 * w1 + w2 + wh + 64 > 256 * 1024 || 3 * w1 + w2 + wh > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
+        uint8_t* dws = (uint8_t*)k->dWsum; uint8_t* hws = c->pinned;
+        uint64_t* hcounts = (uint64_t*)(c->pinned + 3 * w1 + w2 + wh);
+        // the main stream produced dW (H2D) and the H scalars so far; fork after the witness upload is visible
+        CU(c, cudaEventRecord(c->pev[0], s0));
+        for (int i = 0; i < 4; i++) if (sx[i] != s0) CU(c, cudaStreamWaitEvent(sx[i], c->pev[0], 0));
+        MsmSorted sw;
+        rc = msm_sort_entries((const uint8_t*)k->dW + wlo * 32, 32, wcnt, gw, c->sort_scratch, sx[0], &sw, &c->stats);
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
+        CU(c, cudaEventRecord(c->pev[1], sx[0]));
+        for (int i = 1; i < 4; i++) if (sx[i] != sx[0]) CU(c, cudaStreamWaitEvent(sx[i], c->pev[1], 0));
+        struct Job { const GroupOps* G; const void* bases; size_t off; size_t len; uint8_t* dst; int tag; };
+        Job jobs[4] = {{&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wlo * G1.aff_bytes), 0, w1, pA, SB_G1},
+                       {&G1, pre ? k->tB1 : (const void*)((const uint8_t*)k->dB1 + wlo * G1.aff_bytes), w1, w1, pB1, SB_G1},
+                       {&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wlo * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2},
+                       {&G1, pre ? k->tC : (const void*)((const uint8_t*)k->dC + wlo * G1.aff_bytes), 2 * w1, w1, pC, SB_G1}};
+        for (int i = 0; i < 4; i++) {
+            c->stats.cur_tag = jobs[i].tag;
+            rc = jobs[i].G->buckets(jobs[i].bases, sw, c->bscr[i], sx[i], dws + jobs[i].off, &c->stats);
+            if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
+            CU(c, cudaMemcpyAsync(hws + jobs[i].off, dws + jobs[i].off, jobs[i].len, cudaMemcpyDeviceToHost, sx[i]));
+            if (i == 0) CU(c, cudaMemcpyAsync(&hcounts[0], sw.counts, 8, cudaMemcpyDeviceToHost, sx[i]));
+            CU(c, cudaEventRecord(c->pev[2 + i], sx[i]));
+        }
+        // QAP -> iNTT -> coset NTT -> join on the main stream, concurrently with the witness MSMs
+        rc = run_qap_ntt(); if (rc) return rc;
+        tick(c, 2);
+        MsmSorted sh;
+        rc = msm_sort_entries((const uint8_t*)tmp + hlo * 32, 32, hcnt, gh, c->sort_scratch2, s0, &sh, &c->stats);
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
+        c->stats.cur_tag = SB_G1;
+        rc = G1.buckets(pre ? k->tH : (const void*)((const uint8_t*)k->dH + hlo * G1.aff_bytes), sh, c->bscr[4], s0, dws + 3 * w1 + w2, &c->stats);
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
+        CU(c, cudaMemcpyAsync(hws + 3 * w1 + w2, dws + 3 * w1 + w2, wh, cudaMemcpyDeviceToHost, s0));
+        CU(c, cudaMemcpyAsync(&hcounts[1], sh.counts, 8, cudaMemcpyDeviceToHost, s0));
+        CU(c, cudaEventRecord(c->pev[6], s0));
+        tick(c, 3);
+        // host recombination as each MSM lands (overlaps with the MSMs still running)
+        for (int i = 0; i < 4; i++) {
+            CU(c, cudaEventSynchronize(c->pev[2 + i]));
+            jobs[i].G->combine(hws + jobs[i].off, gw, jobs[i].dst);
+        }
+        CU(c, cudaEventSynchronize(c->pev[6]));
+        G1.combine(hws + 3 * w1 + w2, gh, pH);
+        // join the auxiliary streams back into the main stream
+        for (int i = 0; i < 4; i++) if (sx[i] != s0) CU(c, cudaStreamWaitEvent(s0, c->pev[2 + i], 0));
+        c->stat[4] += 3.0 * (double)hcounts[0] + (double)hcounts[1]; c->stat[5] += (double)hcounts[0];
+    } else {
+    rc = run_qap_ntt(); if (rc) return rc;
+    tick(c, 2);
     for (uint64_t off = 0; off < wcnt; off += MAXC) {
         uint64_t cn = std::min(MAXC, wcnt - off), base = wlo + off;
         MsmGeom g = msm_geometry(cn, 32);
@@ -770,10 +884,10 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         G1.combine(hw.data(), g, pA); G1.combine(hw.data() + w1, g, pB1); G1.combine(hw.data() + 2 * w1, g, pC); G2.combine(hw.data() + 3 * w1, g, pB2);
     }
     tick(c, 3);
-    uint64_t hlo, hcnt; range(n, hlo, hcnt);
     if (hcnt) {
         rc = msm_dev_accumulate(c, G1, (const uint8_t*)k->dH + hlo * G1.aff_bytes, (const uint8_t*)tmp + hlo * 32, 32, hcnt, pH);
         if (rc) return rc;
+    }
     }
     tick(c, 4);
     cudaEventSynchronize(c->ev[4]);

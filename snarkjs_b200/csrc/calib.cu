@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256) k_calib_imad(uint64_t* out, int iters, ui
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x), "r"(y));
+            for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"((uint32_t)acc[(j + 3) & 7]), "r"(y));   // data dependent multiplicand: no strength reduction
         }
     }
     uint64_t s = 0;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_calib_imad(uint64_t* out, int iters, ui
 __global__ void __launch_bounds__(256) k_calib_modmul(uint32_t* out, int iters) {
     typedef Fp<BnFq> F;
     F a = F::one(), b = F::r2(), c = F::one(), d = F::r2();
-    a.v[0] += threadIdx.x; c.v[1] += blockIdx.x;
+    a.v[0] += threadIdx.x; c.v[1] += blockIdx.x + 3 * threadIdx.x; b.v[2] ^= threadIdx.x; d.v[3] += 7 * threadIdx.x;   // every chain is per-thread (nothing for the uniform datapath)
     for (int it = 0; it < iters; it++) { a = F::mul(a, b); c = F::mul(c, d); b = F::mul(b, a); d = F::mul(d, c); }
     F r = F::add(F::add(a, b), F::add(c, d));
     out[blockIdx.x * blockDim.x + threadIdx.x] = r.v[0] ^ r.v[7];

@@ -258,21 +258,32 @@ _Pragma("unroll")
     // Host-side multiply (final proof assembly, window Horner): plain word-serial Montgomery with 64-bit
     // accumulators.  Same canonical result as the device path.
     static inline Fp host_mul(const Fp& a, const Fp& b) {
-        uint32_t t[N + 2];
-        for (int i = 0; i < N + 2; i++) t[i] = 0;
-        for (int i = 0; i < N; i++) {
-            uint64_t c = 0;
-            for (int j = 0; j < N; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
-            c += t[N]; t[N] = (uint32_t)c; t[N + 1] = (uint32_t)(c >> 32);
-            uint32_t m = t[0] * P::np0;
-            c = ((uint64_t)m * P::p(0) + t[0]) >> 32;
-            for (int j = 1; j < N; j++) { c += (uint64_t)m * P::p(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
-            c += t[N]; t[N - 1] = (uint32_t)c; t[N] = t[N + 1] + (uint32_t)(c >> 32);
+        constexpr int M = N / 2;                       // 64-bit limbs
+        typedef unsigned __int128 u128;
+        uint64_t A[M], B[M], Pm[M], t[M + 2];
+        for (int i = 0; i < M; i++) {
+            A[i] = a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+            B[i] = b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+            Pm[i] = P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32);
         }
-        Fp r; bool ge = t[N] != 0;
-        if (!ge) { ge = true; for (int i = N - 1; i >= 0; i--) { if (t[i] > P::p(i)) break; if (t[i] < P::p(i)) { ge = false; break; } } }
-        if (ge) { uint64_t bw = 0; for (int i = 0; i < N; i++) { uint64_t d = (uint64_t)t[i] - P::p(i) - bw; r.v[i] = (uint32_t)d; bw = (d >> 32) & 1; } }
-        else for (int i = 0; i < N; i++) r.v[i] = t[i];
+        for (int i = 0; i < M + 2; i++) t[i] = 0;
+        uint64_t inv = (uint32_t)(0u - P::np0);        // p^-1 mod 2^32, one Newton step -> mod 2^64
+        inv *= 2 - Pm[0] * inv;
+        const uint64_t n0 = 0 - inv;
+        for (int i = 0; i < M; i++) {
+            u128 c = 0;
+            for (int j = 0; j < M; j++) { c += (u128)A[j] * B[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[M]; t[M] = (uint64_t)c; t[M + 1] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * n0;
+            c = ((u128)m * Pm[0] + t[0]) >> 64;
+            for (int j = 1; j < M; j++) { c += (u128)m * Pm[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[M]; t[M - 1] = (uint64_t)c; t[M] = t[M + 1] + (uint64_t)(c >> 64);
+        }
+        bool ge = t[M] != 0;
+        if (!ge) { ge = true; for (int i = M - 1; i >= 0; i--) { if (t[i] > Pm[i]) break; if (t[i] < Pm[i]) { ge = false; break; } } }
+        if (ge) { u128 bw = 0; for (int i = 0; i < M; i++) { u128 d = (u128)t[i] - Pm[i] - bw; t[i] = (uint64_t)d; bw = (d >> 64) & 1; } }
+        Fp r;
+        for (int i = 0; i < M; i++) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
         return r;
     }
 #endif

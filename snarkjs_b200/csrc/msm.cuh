@@ -26,10 +26,18 @@ namespace sb {
 
 static constexpr int MSM_SEG = 32;          // sorted entries per thread in k_accumulate / k_fold
 static constexpr int MSM_ACC_THREADS = 128;
-static constexpr int MSM_RED_CHUNK = 32;    // buckets per thread in k_reduce
+static constexpr int MSM_RED_CHUNK = 16;    // buckets per thread in k_reduce
 static constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
 
 
+// geometry of the precomputed-window mode for a registered set of n_set points
+__host__ inline MsmGeom msm_geometry_precomp(uint64_t n_set, uint32_t scalar_bytes) {
+    int l2 = 0; while ((1ull << (l2 + 1)) <= n_set) l2++;
+    int c = l2 - 1; if (c < 8) c = 8; if (c > 22) c = 22;
+    MsmGeom g; g.c = c; g.W = (int)((8 * scalar_bytes + 1 + c - 1) / c); g.B = 1u << (c - 1);
+    g.precomp = 1; g.stride = n_set; g.first = 0;
+    return g;
+}
 __host__ inline MsmGeom msm_geometry(uint64_t n, uint32_t scalar_bytes) {
     int l2 = 0; while ((1ull << (l2 + 1)) <= n) l2++;
     int c = l2 - 4; if (c < 3) c = 3; if (c > 18) c = 18;
@@ -66,8 +74,8 @@ template <class T> __device__ __forceinline__ T load_vec(const T* src) {
 // ------------------------------------------------------------------------------------------------
 // level 0: affine bases gathered through the sorted (key, val) list
 // ------------------------------------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(MSM_ACC_THREADS)
+template <class F, int MINB>
+__global__ void __launch_bounds__(MSM_ACC_THREADS, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const uint64_t* __restrict__ counts, XYZZ<F>* __restrict__ buckets,
              XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
@@ -99,7 +107,40 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ k
 }
 
 // ------------------------------------------------------------------------------------------------
-// level >= 1: fold head partials (sorted by key by construction).  `last` = single-thread final level.
+// level 1 fast path: one thread per head partial.  Heads are sorted by key; a run of equal keys of length
+// <= MSM_SHORT_RUN is summed by its first thread and added to the bucket (for uniform scalars practically every
+// run has length 1, so this is one fully parallel read-modify-write per head).  Heads consumed here are marked
+// INVALID in keys_out; longer runs (skewed scalars: giant buckets) keep their key and go to the k_fold cascade.
+// ------------------------------------------------------------------------------------------------
+static constexpr int MSM_SHORT_RUN = 4;
+template <class F>
+__global__ void __launch_bounds__(MSM_ACC_THREADS)
+k_fold_short(const XYZZ<F>* __restrict__ heads, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+             const uint64_t* __restrict__ counts, XYZZ<F>* __restrict__ buckets) {
+    const uint64_t M = counts[1];
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    const uint32_t k = keys_in[t];
+    // locate the start of my run (looking back at most MSM_SHORT_RUN entries)
+    uint64_t start = t; int back = 0;
+    while (start > 0 && back < MSM_SHORT_RUN && keys_in[start - 1] == k) { start--; back++; }
+    bool is_short = back < MSM_SHORT_RUN;
+    uint64_t len = 0;
+    if (is_short) {
+        len = 1;
+        while (start + len < M && len <= (uint64_t)MSM_SHORT_RUN && keys_in[start + len] == k) len++;
+        is_short = len <= (uint64_t)MSM_SHORT_RUN;
+    }
+    keys_out[t] = is_short ? MSM_INVALID_KEY : k;
+    if (!is_short || start != t) return;
+    XYZZ<F> acc = load_vec(buckets + k);
+    for (uint64_t e = 0; e < len; e++) { XYZZ<F> p = load_vec(heads + t + e); acc.add(p); }
+    store_vec(buckets + k, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// level >= 1 cascade: fold the remaining head partials (sorted by key, INVALID = already consumed).
+// `last` = single-thread final level.
 // ------------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(MSM_ACC_THREADS)
@@ -114,18 +155,16 @@ k_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, con
     XYZZ<F> acc = XYZZ<F>::inf();
     uint32_t cur = in_keys[lo];
     bool first = !last;
+    auto flush = [&]() {
+        if (first) { store_vec(heads + t, acc); head_keys[t] = cur; first = false; }
+        else if (cur != MSM_INVALID_KEY) { XYZZ<F> b = load_vec(buckets + cur); b.add(acc); store_vec(buckets + cur, b); }
+    };
     for (uint64_t e = lo; e < hi; e++) {
         uint32_t k = in_keys[e];
-        if (k != cur) {
-            if (first) { store_vec(heads + t, acc); head_keys[t] = cur; first = false; }
-            else { XYZZ<F> b = load_vec(buckets + cur); b.add(acc); store_vec(buckets + cur, b); }
-            acc = XYZZ<F>::inf(); cur = k;
-        }
-        XYZZ<F> p = load_vec(in + e);
-        acc.add(p);
+        if (k != cur) { flush(); acc = XYZZ<F>::inf(); cur = k; }
+        if (k != MSM_INVALID_KEY) { XYZZ<F> p = load_vec(in + e); acc.add(p); }
     }
-    if (first) { store_vec(heads + t, acc); head_keys[t] = cur; }
-    else { XYZZ<F> b = load_vec(buckets + cur); b.add(acc); store_vec(buckets + cur, b); }
+    flush();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -177,14 +216,45 @@ k_reduce(const XYZZ<F>* __restrict__ buckets, MsmGeom g, XYZZ<F>* __restrict__ p
     if (threadIdx.x == 0) store_vec(partials + (uint64_t)w * ctas_per_window + cta, load_vec(sm));
 }
 
-// one CTA per window: sum the per-CTA partials of k_reduce
+// one warp per window: lanes stride over the per-CTA partials of k_reduce, then a shared-memory tree
 template <class F>
 __global__ void __launch_bounds__(32)
 k_window_sum(const XYZZ<F>* __restrict__ partials, uint32_t per_window, XYZZ<F>* __restrict__ out) {
-    if (threadIdx.x) return;
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = 0; i < per_window; i++) { XYZZ<F> p = load_vec(partials + (uint64_t)blockIdx.x * per_window + i); acc.add(p); }
-    store_vec(out + blockIdx.x, acc);
+    for (uint32_t i = threadIdx.x; i < per_window; i += 32) { XYZZ<F> p = load_vec(partials + (uint64_t)blockIdx.x * per_window + i); acc.add(p); }
+    store_vec(sm + threadIdx.x, acc);
+    __syncwarp();
+    for (uint32_t s = 16; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { XYZZ<F> a = load_vec(sm + threadIdx.x), b = load_vec(sm + threadIdx.x + s); a.add(b); store_vec(sm + threadIdx.x, a); }
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) store_vec(out + blockIdx.x, load_vec(sm));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Precomputed window multiples for a registered base set: table[w*n + i] = 2^(c*w) * P_i (affine), w < W.
+// One thread per point: c doublings per window in XYZZ, one inversion per table entry.  One-time cost per key.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_precompute(const Affine<F>* __restrict__ bases, uint64_t n, int c, int W, Affine<F>* __restrict__ table) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> a = load_vec(bases + i);
+    store_vec(table + i, a);
+    if (a.is_inf()) {
+        for (int w = 1; w < W; w++) store_vec(table + (uint64_t)w * n + i, a);
+        return;
+    }
+    XYZZ<F> p; p.x = a.x; p.y = a.y; p.zz = F::one(); p.zzz = F::one();
+    for (int w = 1; w < W; w++) {
+        for (int j = 0; j < c; j++) p = XYZZ<F>::dbl(p);
+        Affine<F> o;
+        if (p.is_inf()) { o.x = F::zero(); o.y = F::zero(); }
+        else { F t = F::inv(F::mul(p.zz, p.zzz)); o.x = F::mul(p.x, F::mul(t, p.zzz)); o.y = F::mul(p.y, F::mul(t, p.zz)); p.x = o.x; p.y = o.y; p.zz = F::one(); p.zzz = F::one(); }
+        store_vec(table + (uint64_t)w * n + i, o);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -223,6 +293,8 @@ struct MsmScratch {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+extern int g_msm_tuning[8];
+
 struct MsmLaunchStats {
     int launches = 0;
     // optional profiling: event pairs recorded around each k_accumulate launch (tag = group id)
@@ -245,7 +317,8 @@ template <class F>
 int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream,
                 XYZZ<F>* d_wsum, MsmLaunchStats* stats) {
     const MsmGeom g = s.g;
-    const uint64_t nbuckets = (uint64_t)g.W * g.B;
+    const uint32_t NW = g.windows();
+    const uint64_t nbuckets = (uint64_t)NW * g.B;
     const uint64_t heads0 = (s.total + MSM_SEG - 1) / MSM_SEG;
     const uint64_t heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
     const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
@@ -256,25 +329,37 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     size_t o_buckets = 0;
     size_t o_headsA = o_buckets + al(nbuckets * sizeof(XYZZ<F>)), o_hkA = o_headsA + al(heads0 * sizeof(XYZZ<F>));
     size_t o_headsB = o_hkA + al(heads0 * 4), o_hkB = o_headsB + al(heads1 * sizeof(XYZZ<F>));
-    size_t o_part = o_hkB + al(heads1 * 4);
-    size_t bytes = o_part + al((size_t)g.W * ctas_per_window * sizeof(XYZZ<F>));
+    size_t o_hkM = o_hkB + al(heads1 * 4);                     // level-1 keys after the short-run fast path
+    size_t o_part = o_hkM + al(heads0 * 4);
+    size_t bytes = o_part + al((size_t)NW * ctas_per_window * sizeof(XYZZ<F>));
     uint8_t* base = (uint8_t*)scratch.get(bytes);
     if (!base) return (int)cudaErrorMemoryAllocation;
     XYZZ<F>* buckets = (XYZZ<F>*)(base + o_buckets);
     XYZZ<F>* headsA = (XYZZ<F>*)(base + o_headsA); uint32_t* hkA = (uint32_t*)(base + o_hkA);
     XYZZ<F>* headsB = (XYZZ<F>*)(base + o_headsB); uint32_t* hkB = (uint32_t*)(base + o_hkB);
     XYZZ<F>* partials = (XYZZ<F>*)(base + o_part);
+    uint32_t* hkM = (uint32_t*)(base + o_hkM);
     int launches = 0;
     cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), stream);
     if (heads0) {
         const bool prof = stats && stats->ev && stats->used + 2 <= stats->nev && stats->used / 2 < 32;
         if (prof) cudaEventRecord(stats->ev[stats->used], stream);
-        k_accumulate<F><<<(unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
-            d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); launches++;
+        {
+            const unsigned grid = (unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+            switch (g_msm_tuning[0]) {   // experimental occupancy variants (sb_set_tuning(0, minBlocksPerSM))
+            case 5: k_accumulate<F, 5><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+            case 6: k_accumulate<F, 6><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+            case 8: k_accumulate<F, 8><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+            default: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+            }
+            launches++;
+        }
         if (prof) { cudaEventRecord(stats->ev[stats->used + 1], stream); stats->tag[stats->used / 2] = stats->cur_tag; stats->used += 2; }
+        k_fold_short<F><<<(unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
+            headsA, hkA, hkM, s.counts, buckets); launches++;
         // fold cascade: level l consumes counts[l] heads (upper bound m on the host, exact count on the device)
         uint64_t m = heads0; int level = 1;
-        XYZZ<F>* hin = headsA; uint32_t* kin = hkA; XYZZ<F>* hout = headsB; uint32_t* kout = hkB;
+        XYZZ<F>* hin = headsA; uint32_t* kin = hkM; XYZZ<F>* hout = headsB; uint32_t* kout = hkB;
         while (true) {
             uint64_t threads = (m + MSM_SEG - 1) / MSM_SEG;
             k_fold<F><<<(unsigned)((threads + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
@@ -285,8 +370,8 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
             if (level >= 8) return (int)cudaErrorUnknown;
         }
     }
-    k_reduce<F><<<g.W * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
-    k_window_sum<F><<<g.W, 32, 0, stream>>>(partials, ctas_per_window, d_wsum); launches++;
+    k_reduce<F><<<NW * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
+    k_window_sum<F><<<NW, 32, 32 * sizeof(XYZZ<F>), stream>>>(partials, ctas_per_window, d_wsum); launches++;
     if (stats) stats->launches += launches;
     return (int)cudaGetLastError();
 }

@@ -8,9 +8,12 @@ int bls12381_g1_buckets(const void* d_bases, const MsmSorted& s, MsmScratch& scr
     return msm_buckets<FT>((const Affine<FT>*)d_bases, s, scratch, stream, (PT*)d_wsum, stats);
 }
 void bls12381_g1_combine(const uint8_t* wsum_host, const MsmGeom& g, uint8_t* acc_xyzz) {
-    std::vector<PT> ws(g.W); memcpy(ws.data(), wsum_host, (size_t)g.W * sizeof(PT));
     PT acc; memcpy(&acc, acc_xyzz, sizeof acc);
-    msm_combine_host<FT>(ws.data(), g, acc);
+    if (g.precomp) { PT r; memcpy(&r, wsum_host, sizeof r); acc.add(r); }   // single shared bucket set: no Horner
+    else {
+        std::vector<PT> ws(g.W); memcpy(ws.data(), wsum_host, (size_t)g.W * sizeof(PT));
+        msm_combine_host<FT>(ws.data(), g, acc);
+    }
     memcpy(acc_xyzz, &acc, sizeof acc);
 }
 void bls12381_g1_add(uint8_t* acc_xyzz, const uint8_t* other_xyzz) {
@@ -38,6 +41,10 @@ void bls12381_g1_times(const uint8_t* xyzz, const uint8_t* k, int nbytes, uint8_
 int bls12381_g1_gen_points(const uint8_t* gen_affine, uint64_t seed, uint64_t n, void* d_out, cudaStream_t stream) {
     Affine<FT> g; memcpy(&g, gen_affine, sizeof g);
     if (n) k_gen_points<FT><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g, seed, n, (Affine<FT>*)d_out);
+    return (int)cudaGetLastError();
+}
+int bls12381_g1_precompute(const void* d_bases, uint64_t n, int c, int W, void* d_table, cudaStream_t stream) {
+    if (n) k_precompute<FT><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>((const Affine<FT>*)d_bases, n, c, W, (Affine<FT>*)d_table);
     return (int)cudaGetLastError();
 }
 uint32_t bls12381_g1_xyzz_bytes() { return (uint32_t)sizeof(PT); }

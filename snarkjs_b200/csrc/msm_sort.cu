@@ -4,6 +4,8 @@
 
 namespace sb {
 
+int g_msm_tuning[8] = {0};
+
 // ------------------------------------------------------------------------------------------------
 // digits: thread i recodes scalar i into W signed digits (reference _getChunk extracts unsigned chunks;
 // signed recoding halves the bucket count and is free because negating an affine point is free).
@@ -34,7 +36,8 @@ __global__ void k_digits(const uint8_t* __restrict__ scalars, uint32_t sbytes, u
         uint32_t raw = ((uint32_t)(two >> sh) & cmask) + carry;
         uint32_t key, val = (uint32_t)i;
         if (raw > half) { raw = (1u << g.c) - raw; carry = 1; val |= 0x80000000u; } else carry = 0;
-        key = raw ? (uint32_t)w * g.B + raw - 1 : MSM_INVALID_KEY;
+        if (g.precomp) { key = raw ? raw - 1 : MSM_INVALID_KEY; val = (uint32_t)((uint64_t)w * g.stride + g.first + i) | (val & 0x80000000u); }
+        else key = raw ? (uint32_t)w * g.B + raw - 1 : MSM_INVALID_KEY;
         keys[(uint64_t)w * n + i] = key;
         vals[(uint64_t)w * n + i] = val;
     }
@@ -57,7 +60,7 @@ __global__ void k_count_valid(const uint32_t* __restrict__ keys, uint64_t total,
 int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmGeom g, MsmScratch& scratch,
                      cudaStream_t stream, MsmSorted* out, MsmLaunchStats* stats) {
     const uint64_t total = n * (uint64_t)g.W;
-    const uint64_t nbuckets = (uint64_t)g.W * g.B;
+    const uint64_t nbuckets = (uint64_t)g.windows() * g.B;
     if (sbytes == 0 || sbytes > 64) return (int)cudaErrorInvalidValue;
     int key_bits = 1; while ((1ull << key_bits) < nbuckets) key_bits++;
     int end_bit = key_bits + 1 > 32 ? 32 : key_bits + 1;   // INVALID (all ones) sorts after every valid key
