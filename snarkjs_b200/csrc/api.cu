@@ -2,6 +2,7 @@
 // drop-in bulk operations, and the fused Groth16 prover.  Host-side orchestration only; kernels live in
 // msm*.cu / fr_kernels.cu.  There is no CPU fallback: without a CUDA device sb_create fails.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,7 +31,7 @@ struct DevBuf {
 
 // group vtable (one per curve x group)
 struct GroupOps {
-    int (*buckets)(const void*, const MsmSorted&, MsmScratch&, cudaStream_t, void*, MsmLaunchStats*);
+    int (*buckets)(const void*, const MsmSorted&, MsmScratch&, cudaStream_t, void*, MsmLaunchStats*, cudaStream_t, cudaEvent_t);
     void (*combine)(const uint8_t*, const MsmGeom&, uint8_t*);
     void (*add)(uint8_t*, const uint8_t*);
     void (*to_jacobian)(const uint8_t*, uint8_t*);
@@ -70,7 +71,7 @@ struct sb_ctx {
     GroupOps g1, g2;
     MsmScratch sort_scratch, bucket_scratch;
     MsmScratch sort_scratch2, bscr[5];           // per-MSM scratch for the overlapped Groth16 pipeline
-    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // high-priority side streams (tails, NTT chain)
     cudaEvent_t pev[16];                         // pipeline events
     uint8_t* pinned = nullptr;                   // 256 KiB pinned staging (window sums, counters)
     MsmLaunchStats stats;
@@ -84,7 +85,7 @@ struct sb_ctx {
     std::vector<Groth16Key*> keys;
     cudaEvent_t ev[8];
     float last_ms[8] = {0};
-    int fr_s = 0;
+    int fr_s = 0, fr_bits = 254;
     std::vector<std::vector<uint8_t>> roots;   // w[0..s] Montgomery bytes
     std::vector<uint8_t> nqr, shift;
     std::vector<uint8_t> gen1, gen2;            // affine generators, Montgomery
@@ -269,13 +270,13 @@ void prof_end(sb_ctx* c) {
 
 // Precomputed window tables (msm.cuh k_precompute).  Built for sets of >= 2^12 points whose table index fits the
 // 31-bit entry value; g_msm_tuning[3] != 0 disables them (plain windowed Pippenger on the raw bases).
-bool want_precomp(uint64_t n) {
+bool want_precomp(sb_ctx* c, uint64_t n) {
     if (g_msm_tuning[3] != 0 || n < (1ull << 12)) return false;
-    MsmGeom g = msm_geometry_precomp(n, 32);
+    MsmGeom g = msm_geometry_precomp(n, 32, c->fr_bits);
     return (uint64_t)g.W * n < (1ull << 31);
 }
 int build_table(sb_ctx* c, const GroupOps& G, const void* d_bases, uint64_t n, void** table, MsmGeom* gp) {
-    MsmGeom g = msm_geometry_precomp(n, 32);
+    MsmGeom g = msm_geometry_precomp(n, 32, c->fr_bits);
     cudaError_t e = cudaMalloc(table, (size_t)g.W * n * G.aff_bytes);
     if (e != cudaSuccess) { *table = nullptr; return cuda_fail(c, e, "precompute table allocation"); }
     int rc = G.precompute(d_bases, n, g.c, g.W, *table, c->stream); c->launches++;
@@ -298,7 +299,7 @@ int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const 
     static const uint64_t MAXC = 1ull << 23;
     for (uint64_t off = 0; off < n; off += MAXC) {
         uint64_t cn = std::min(MAXC, n - off);
-        MsmGeom g = msm_geometry(cn, sbytes);
+        MsmGeom g = msm_geometry(cn, sbytes, c->fr_bits);
         if (gp) {   // registered set with precomputed window multiples: d_bases is the table
             g = *gp; g.first = first + off; g.W = (int)((8 * sbytes + 1 + g.c - 1) / g.c);
         }
@@ -308,7 +309,7 @@ int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const 
         void* d_wsum = c->io[3].get((size_t)g.windows() * G.xyzz_bytes);
         if (!d_wsum) return fail(c, SB_ERR_NOMEM, "out of device memory");
         c->stats.cur_tag = (&G == &c->g1) ? SB_G1 : SB_G2;
-        rc = G.buckets(gp ? d_bases : (const void*)((const uint8_t*)d_bases + off * G.aff_bytes), s, c->bucket_scratch, c->stream, d_wsum, &c->stats);
+        rc = G.buckets(gp ? d_bases : (const void*)((const uint8_t*)d_bases + off * G.aff_bytes), s, c->bucket_scratch, c->stream, d_wsum, &c->stats, nullptr, nullptr);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
         std::vector<uint8_t> ws((size_t)g.windows() * G.xyzz_bytes);
         uint64_t entries = 0;
@@ -408,13 +409,15 @@ int sb_create(int curve, int device_id, sb_ctx** out) {
     sb_ctx* c = new sb_ctx();
     c->curve = curve; c->device = device_id;
     c->n8q = curve == SB_BN254 ? 32 : 48;
+    c->fr_bits = curve == SB_BN254 ? 254 : 255;
     if (curve == SB_BN254) { c->g1 = SB_GROUP_OPS(bn254_g1, 64); c->g2 = SB_GROUP_OPS(bn254_g2, 128); }
     else { c->g1 = SB_GROUP_OPS(bls12381_g1, 96); c->g2 = SB_GROUP_OPS(bls12381_g2, 192); }
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return SB_ERR_CUDA; }
     for (auto& e : c->ev) cudaEventCreate(&e);
     for (auto& e : c->prof_ev) cudaEventCreate(&e);
     for (auto& e : c->pev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    for (auto& st : c->aux) cudaStreamCreate(&st);
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      for (auto& st : c->aux) cudaStreamCreateWithPriority(&st, cudaStreamDefault, hi); }
     if (cudaHostAlloc((void**)&c->pinned, 256 * 1024, cudaHostAllocDefault) != cudaSuccess) c->pinned = nullptr;
     init_generators(c);
     int rc = curve == SB_BN254 ? init_roots<BnFr>(c) : init_roots<BlsFr>(c);
@@ -466,7 +469,7 @@ int sb_bases_register(sb_ctx* c, int group, const uint8_t* bases, uint64_t n, ui
     BaseSet b; b.group = group; b.n = n;
     CU(c, cudaMalloc(&b.d, n ? n * G.aff_bytes : 16));
     CU(c, cudaMemcpy(b.d, bases, n * G.aff_bytes, cudaMemcpyHostToDevice));
-    if (want_precomp(n)) { int rc = build_table(c, G, b.d, n, &b.table, &b.gp); if (rc) { cudaFree(b.d); return rc; } }
+    if (want_precomp(c, n)) { int rc = build_table(c, G, b.d, n, &b.table, &b.gp); if (rc) { cudaFree(b.d); return rc; } }
     c->bases.push_back(b);
     *handle = c->bases.size();
     return 0;
@@ -718,7 +721,7 @@ int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle
     up(&k->dA_T, nullptr, 0, n * 32); up(&k->dB_T, nullptr, 0, n * 32); up(&k->dC_T, nullptr, 0, n * 32); up(&k->dTmp, nullptr, 0, n * 32);
     up(&k->dWsum, nullptr, 0, 8 * 80 * 4 * 96);
     if (e != cudaSuccess) { free_key(k); return cuda_fail(c, e, "sb_groth16_load upload"); }
-    if (want_precomp(nv) && want_precomp(n)) {
+    if (want_precomp(c, nv) && want_precomp(c, n)) {
         int rc2 = build_table(c, c->g1, k->dA, nv, &k->tA, &k->gpW);
         if (!rc2) rc2 = build_table(c, c->g1, k->dB1, nv, &k->tB1, &k->gpW);
         if (!rc2) rc2 = build_table(c, c->g2, k->dB2, nv, &k->tB2, &k->gpW);
@@ -805,64 +808,78 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         // concurrently on the main stream.  g_msm_tuning[2] != 0 serialises everything on one stream (profiling).
         const bool serial = g_msm_tuning[2] != 0;
         cudaStream_t s0 = c->stream;
-        cudaStream_t sx[4] = {serial ? s0 : c->aux[0], serial ? s0 : c->aux[1], serial ? s0 : c->aux[2], serial ? s0 : c->aux[3]};
-        MsmGeom gw = msm_geometry(wcnt, 32), gh = msm_geometry(hcnt, 32);
+        // schedule: main stream  : H2D, sort(witness), acc B2, acc A, acc B1, acc C, [join NTT chain], acc H
+        //           aux[5] (hi)  : QAP -> iNTT -> coset NTT -> joinABC -> sort(H scalars)
+        //           aux[0..4](hi): the latency-bound tail of each MSM (fold, reduce, window sum, D2H)
+        cudaStream_t sN = serial ? s0 : c->aux[5];
+        MsmGeom gw = msm_geometry(wcnt, 32, c->fr_bits), gh = msm_geometry(hcnt, 32, c->fr_bits);
         const bool pre = k->tA != nullptr;
         if (pre) { gw = k->gpW; gw.first = wlo; gh = k->gpH; gh.first = hlo; }
         const size_t w1 = (size_t)gw.windows() * G1.xyzz_bytes, w2 = (size_t)gw.windows() * G2.xyzz_bytes, wh = (size_t)gh.windows() * G1.xyzz_bytes;
         if (3 * w1 + w2 + wh + 64 > 256 * 1024 || 3 * w1 + w2 + wh > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
         uint8_t* dws = (uint8_t*)k->dWsum; uint8_t* hws = c->pinned;
         uint64_t* hcounts = (uint64_t*)(c->pinned + 3 * w1 + w2 + wh);
-        // the main stream produced dW (H2D) and the H scalars so far; fork after the witness upload is visible
-        CU(c, cudaEventRecord(c->pev[0], s0));
-        for (int i = 0; i < 4; i++) if (sx[i] != s0) CU(c, cudaStreamWaitEvent(sx[i], c->pev[0], 0));
-        MsmSorted sw;
-        rc = msm_sort_entries((const uint8_t*)k->dW + wlo * 32, 32, wcnt, gw, c->sort_scratch, sx[0], &sw, &c->stats);
-        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
-        CU(c, cudaEventRecord(c->pev[1], sx[0]));
-        for (int i = 1; i < 4; i++) if (sx[i] != sx[0]) CU(c, cudaStreamWaitEvent(sx[i], c->pev[1], 0));
-        struct Job { const GroupOps* G; const void* bases; size_t off; size_t len; uint8_t* dst; int tag; };
-        Job jobs[4] = {{&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wlo * G1.aff_bytes), 0, w1, pA, SB_G1},
-                       {&G1, pre ? k->tB1 : (const void*)((const uint8_t*)k->dB1 + wlo * G1.aff_bytes), w1, w1, pB1, SB_G1},
-                       {&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wlo * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2},
-                       {&G1, pre ? k->tC : (const void*)((const uint8_t*)k->dC + wlo * G1.aff_bytes), 2 * w1, w1, pC, SB_G1}};
-        for (int i = 0; i < 4; i++) {
-            c->stats.cur_tag = jobs[i].tag;
-            rc = jobs[i].G->buckets(jobs[i].bases, sw, c->bscr[i], sx[i], dws + jobs[i].off, &c->stats);
-            if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
-            CU(c, cudaMemcpyAsync(hws + jobs[i].off, dws + jobs[i].off, jobs[i].len, cudaMemcpyDeviceToHost, sx[i]));
-            if (i == 0) CU(c, cudaMemcpyAsync(&hcounts[0], sw.counts, 8, cudaMemcpyDeviceToHost, sx[i]));
-            CU(c, cudaEventRecord(c->pev[2 + i], sx[i]));
-        }
-        // QAP -> iNTT -> coset NTT -> join on the main stream, concurrently with the witness MSMs
-        rc = run_qap_ntt(); if (rc) return rc;
-        tick(c, 2);
+        CU(c, cudaEventRecord(c->pev[0], s0));                       // witness resident
+        if (sN != s0) CU(c, cudaStreamWaitEvent(sN, c->pev[0], 0));
+        // NTT chain + sort of the H scalars on the side stream
+        cudaStream_t saved = c->stream; c->stream = sN;
+        rc = run_qap_ntt();
         MsmSorted sh;
-        rc = msm_sort_entries((const uint8_t*)tmp + hlo * 32, 32, hcnt, gh, c->sort_scratch2, s0, &sh, &c->stats);
+        if (!rc) { rc = msm_sort_entries((const uint8_t*)tmp + hlo * 32, 32, hcnt, gh, c->sort_scratch2, sN, &sh, &c->stats); if (rc) rc = cuda_fail(c, (cudaError_t)rc, "msm_sort_entries"); }
+        c->stream = saved;
+        if (rc) return rc;
+        CU(c, cudaEventRecord(c->pev[1], sN));
+        static cudaEvent_t tl_ev[8]; static bool tl_init = false;
+        const bool tl = getenv("SB_TIMELINE") != nullptr;
+        if (tl && !tl_init) { for (auto& e : tl_ev) cudaEventCreate(&e); tl_init = true; }
+        if (tl) cudaEventRecord(tl_ev[5], sN);
+        // witness MSMs on the main stream
+        MsmSorted sw;
+        rc = msm_sort_entries((const uint8_t*)k->dW + wlo * 32, 32, wcnt, gw, c->sort_scratch, s0, &sw, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
-        c->stats.cur_tag = SB_G1;
-        rc = G1.buckets(pre ? k->tH : (const void*)((const uint8_t*)k->dH + hlo * G1.aff_bytes), sh, c->bscr[4], s0, dws + 3 * w1 + w2, &c->stats);
-        if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
-        CU(c, cudaMemcpyAsync(hws + 3 * w1 + w2, dws + 3 * w1 + w2, wh, cudaMemcpyDeviceToHost, s0));
-        CU(c, cudaMemcpyAsync(&hcounts[1], sh.counts, 8, cudaMemcpyDeviceToHost, s0));
-        CU(c, cudaEventRecord(c->pev[6], s0));
+        tick(c, 2);
+        struct Job { const GroupOps* G; const void* bases; size_t off; size_t len; uint8_t* dst; int tag; const MsmSorted* srt; const MsmGeom* g; };
+        Job jobs[5] = {{&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wlo * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2, &sw, &gw},
+                       {&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wlo * G1.aff_bytes), 0, w1, pA, SB_G1, &sw, &gw},
+                       {&G1, pre ? k->tB1 : (const void*)((const uint8_t*)k->dB1 + wlo * G1.aff_bytes), w1, w1, pB1, SB_G1, &sw, &gw},
+                       {&G1, pre ? k->tC : (const void*)((const uint8_t*)k->dC + wlo * G1.aff_bytes), 2 * w1, w1, pC, SB_G1, &sw, &gw},
+                       {&G1, pre ? k->tH : (const void*)((const uint8_t*)k->dH + hlo * G1.aff_bytes), 3 * w1 + w2, wh, pH, SB_G1, &sh, &gh}};
+        for (int i = 0; i < 5; i++) {
+            cudaStream_t st = serial ? s0 : c->aux[i];
+            if (i == 4 && sN != s0) CU(c, cudaStreamWaitEvent(s0, c->pev[1], 0));   // H needs the NTT chain
+            c->stats.cur_tag = jobs[i].tag;
+            rc = jobs[i].G->buckets(jobs[i].bases, *jobs[i].srt, c->bscr[i], s0, dws + jobs[i].off, &c->stats, st, c->pev[8 + i]);
+            if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
+            CU(c, cudaMemcpyAsync(hws + jobs[i].off, dws + jobs[i].off, jobs[i].len, cudaMemcpyDeviceToHost, st));
+            if (i == 0) CU(c, cudaMemcpyAsync(&hcounts[0], sw.counts, 8, cudaMemcpyDeviceToHost, st));
+            if (i == 4) CU(c, cudaMemcpyAsync(&hcounts[1], sh.counts, 8, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaEventRecord(c->pev[2 + i], st));
+            if (tl) cudaEventRecord(tl_ev[i], st);
+        }
         tick(c, 3);
         // host recombination as each MSM lands (overlaps with the MSMs still running)
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 5; i++) {
             CU(c, cudaEventSynchronize(c->pev[2 + i]));
-            jobs[i].G->combine(hws + jobs[i].off, gw, jobs[i].dst);
+            jobs[i].G->combine(hws + jobs[i].off, *jobs[i].g, jobs[i].dst);
         }
-        CU(c, cudaEventSynchronize(c->pev[6]));
-        G1.combine(hws + 3 * w1 + w2, gh, pH);
-        // join the auxiliary streams back into the main stream
-        for (int i = 0; i < 4; i++) if (sx[i] != s0) CU(c, cudaStreamWaitEvent(s0, c->pev[2 + i], 0));
+        if (tl) {
+            cudaDeviceSynchronize();
+            float t; cudaEventElapsedTime(&t, c->ev[0], tl_ev[5]); fprintf(stderr, "[timeline] ntt chain + sort H done at %.3f ms\n", t);
+            for (int i = 0; i + 1 < c->stats.used; i += 2) {
+                float a, b; cudaEventElapsedTime(&a, c->ev[0], c->prof_ev[i]); cudaEventElapsedTime(&b, c->ev[0], c->prof_ev[i + 1]);
+                float e; cudaEventElapsedTime(&e, c->ev[0], tl_ev[i / 2]);
+                fprintf(stderr, "[timeline] msm %d: accumulate %.3f -> %.3f ms, tail done %.3f ms\n", i / 2, a, b, e);
+            }
+        }
+        // join the side streams back into the main stream
+        if (!serial) { for (int i = 0; i < 5; i++) CU(c, cudaStreamWaitEvent(s0, c->pev[2 + i], 0)); CU(c, cudaStreamWaitEvent(s0, c->pev[1], 0)); }
         c->stat[4] += 3.0 * (double)hcounts[0] + (double)hcounts[1]; c->stat[5] += (double)hcounts[0];
     } else {
     rc = run_qap_ntt(); if (rc) return rc;
     tick(c, 2);
     for (uint64_t off = 0; off < wcnt; off += MAXC) {
         uint64_t cn = std::min(MAXC, wcnt - off), base = wlo + off;
-        MsmGeom g = msm_geometry(cn, 32);
+        MsmGeom g = msm_geometry(cn, 32, c->fr_bits);
         MsmSorted s;
         rc = msm_sort_entries((const uint8_t*)k->dW + base * 32, 32, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
@@ -870,11 +887,11 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         size_t w1 = (size_t)g.W * G1.xyzz_bytes, w2 = (size_t)g.W * G2.xyzz_bytes;
         if (3 * w1 + w2 > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
         c->stats.cur_tag = SB_G1;
-        rc = G1.buckets((const uint8_t*)k->dA + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm A");
-        rc = G1.buckets((const uint8_t*)k->dB1 + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B1");
-        rc = G1.buckets((const uint8_t*)k->dC + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + 2 * w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm C");
+        rc = G1.buckets((const uint8_t*)k->dA + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws, &c->stats, nullptr, nullptr); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm A");
+        rc = G1.buckets((const uint8_t*)k->dB1 + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + w1, &c->stats, nullptr, nullptr); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B1");
+        rc = G1.buckets((const uint8_t*)k->dC + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws + 2 * w1, &c->stats, nullptr, nullptr); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm C");
         c->stats.cur_tag = SB_G2;
-        rc = G2.buckets((const uint8_t*)k->dB2 + base * G2.aff_bytes, s, c->bucket_scratch, c->stream, ws + 3 * w1, &c->stats); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B2");
+        rc = G2.buckets((const uint8_t*)k->dB2 + base * G2.aff_bytes, s, c->bucket_scratch, c->stream, ws + 3 * w1, &c->stats, nullptr, nullptr); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm B2");
         std::vector<uint8_t> hw(3 * w1 + w2);
         uint64_t entries = 0;
         CU(c, cudaMemcpyAsync(hw.data(), ws, hw.size(), cudaMemcpyDeviceToHost, c->stream));

@@ -30,19 +30,45 @@ static constexpr int MSM_RED_CHUNK = 16;    // buckets per thread in k_reduce
 static constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
 
 
-// geometry of the precomputed-window mode for a registered set of n_set points
-__host__ inline MsmGeom msm_geometry_precomp(uint64_t n_set, uint32_t scalar_bytes) {
+// Window-size choice.  Cost model: W_eff*n mixed adds (10 modmul) + one pass over the buckets (~60 modmul each);
+// buckets = 2^(c-1) per window, shared by all windows in the precomputed-table mode.  `fr_bits` is the bit length of
+// the scalar field (254 / 255): field-element scalars leave the windows above it empty, and the top *occupied* window
+// only has top_bits = fr_bits + 1 - (W_eff-1)*c significant bits, i.e. it funnels all n terms into 2^top_bits buckets.
+// Candidates whose top window is more than 32x denser than the others are skipped (giant buckets are handled
+// correctly by the fold cascade, but cost latency-bound milliseconds).  W itself always covers 8*scalar_bytes + 1 bits,
+// so arbitrary scalars (the reference accepts any value < 2^(8*sScalar)) stay correct.
+__host__ inline MsmGeom msm_choose(uint64_t n, uint32_t scalar_bytes, int fr_bits, bool precomp) {
+    int eff = (int)(8 * scalar_bytes) < fr_bits ? (int)(8 * scalar_bytes) : fr_bits;
+    int best_c = 3; double best = 1e300;
+    for (int c = 3; c <= 22; c++) {
+        int weff = (eff + 1 + c - 1) / c, top = eff + 1 - (weff - 1) * c;
+        if (weff > 1 && top < c - 5) continue;
+        double buckets = (precomp ? 1.0 : (double)weff) * (double)(1u << (c - 1));
+        double cost = (double)weff * (double)n * 10.0 + buckets * 60.0;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    MsmGeom g; g.c = best_c; g.W = (int)((8 * scalar_bytes + 1 + best_c - 1) / best_c); g.B = 1u << (best_c - 1);
+    return g;
+}
+// Precomputed-window mode (tables cover 32-byte scalars): all windows share one bucket set, so the bucket pass is
+// cheap and what matters is the number of windows: take the largest c (fewest windows) that keeps the top window's
+// density within 32x of the others and leaves on average >= ~W entries per bucket (2^(c-1) <= n).  Sparse buckets
+// (a few dozen entries) also keep the per-thread head partials short-run, i.e. on the parallel k_fold_short path.
+__host__ inline MsmGeom msm_geometry_precomp(uint64_t n_set, uint32_t scalar_bytes, int fr_bits = 254) {
     int l2 = 0; while ((1ull << (l2 + 1)) <= n_set) l2++;
-    int c = l2 - 1; if (c < 8) c = 8; if (c > 22) c = 22;
+    int cmax = l2 + 1; if (cmax > 22) cmax = 22; if (cmax < 8) cmax = 8;
+    int c = 8;
+    for (int cc = cmax; cc >= 8; cc--) {
+        int weff = (fr_bits + 1 + cc - 1) / cc, top = fr_bits + 1 - (weff - 1) * cc;
+        if (weff > 1 && top < cc - 5) continue;
+        c = cc; break;
+    }
     MsmGeom g; g.c = c; g.W = (int)((8 * scalar_bytes + 1 + c - 1) / c); g.B = 1u << (c - 1);
     g.precomp = 1; g.stride = n_set; g.first = 0;
     return g;
 }
-__host__ inline MsmGeom msm_geometry(uint64_t n, uint32_t scalar_bytes) {
-    int l2 = 0; while ((1ull << (l2 + 1)) <= n) l2++;
-    int c = l2 - 4; if (c < 3) c = 3; if (c > 18) c = 18;
-    MsmGeom g; g.c = c; g.W = (int)((8 * scalar_bytes + 1 + c - 1) / c); g.B = 1u << (c - 1);
-    return g;
+__host__ inline MsmGeom msm_geometry(uint64_t n, uint32_t scalar_bytes, int fr_bits = 254) {
+    return msm_choose(n, scalar_bytes, fr_bits, false);
 }
 
 template <class F> __device__ __forceinline__ void load_affine(const Affine<F>* __restrict__ bases, uint32_t idx, F& x, F& y) {
@@ -112,7 +138,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ k
 // run has length 1, so this is one fully parallel read-modify-write per head).  Heads consumed here are marked
 // INVALID in keys_out; longer runs (skewed scalars: giant buckets) keep their key and go to the k_fold cascade.
 // ------------------------------------------------------------------------------------------------
-static constexpr int MSM_SHORT_RUN = 4;
+static constexpr int MSM_SHORT_RUN = 8;
 template <class F>
 __global__ void __launch_bounds__(MSM_ACC_THREADS)
 k_fold_short(const XYZZ<F>* __restrict__ heads, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
@@ -313,9 +339,12 @@ int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmG
                      cudaStream_t stream, MsmSorted* out, MsmLaunchStats* stats);
 
 // Bucket accumulation + reduction for one base set.  Writes g.W window sums to d_wsum (device).  Asynchronous.
+// If tail_stream differs from stream, the throughput-bound accumulation runs on `stream` and the latency-bound tail
+// (fold, bucket reduction, window sum) on `tail_stream` after `ev_acc` (recorded here): with a higher-priority tail
+// stream the tail of one MSM slips into the SM slots freed by the next MSM's accumulation instead of queueing behind it.
 template <class F>
 int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream,
-                XYZZ<F>* d_wsum, MsmLaunchStats* stats) {
+                XYZZ<F>* d_wsum, MsmLaunchStats* stats, cudaStream_t tail_stream = nullptr, cudaEvent_t ev_acc = nullptr) {
     const MsmGeom g = s.g;
     const uint32_t NW = g.windows();
     const uint64_t nbuckets = (uint64_t)NW * g.B;
@@ -355,6 +384,9 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
             launches++;
         }
         if (prof) { cudaEventRecord(stats->ev[stats->used + 1], stream); stats->tag[stats->used / 2] = stats->cur_tag; stats->used += 2; }
+        if (tail_stream && tail_stream != stream && ev_acc) {
+            cudaEventRecord(ev_acc, stream); cudaStreamWaitEvent(tail_stream, ev_acc, 0); stream = tail_stream;
+        }
         k_fold_short<F><<<(unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
             headsA, hkA, hkM, s.counts, buckets); launches++;
         // fold cascade: level l consumes counts[l] heads (upper bound m on the host, exact count on the device)
@@ -370,6 +402,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
             if (level >= 8) return (int)cudaErrorUnknown;
         }
     }
+    if (!heads0 && tail_stream && tail_stream != stream && ev_acc) { cudaEventRecord(ev_acc, stream); cudaStreamWaitEvent(tail_stream, ev_acc, 0); stream = tail_stream; }
     k_reduce<F><<<NW * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
     k_window_sum<F><<<NW, 32, 32 * sizeof(XYZZ<F>), stream>>>(partials, ctas_per_window, d_wsum); launches++;
     if (stats) stats->launches += launches;

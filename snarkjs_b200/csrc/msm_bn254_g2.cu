@@ -4,8 +4,9 @@
 namespace sb {
 typedef Fp2<BnFq> FT;
 typedef XYZZ<FT> PT;
-int bn254_g2_buckets(const void* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream, void* d_wsum, MsmLaunchStats* stats) {
-    return msm_buckets<FT>((const Affine<FT>*)d_bases, s, scratch, stream, (PT*)d_wsum, stats);
+int bn254_g2_buckets(const void* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream, void* d_wsum, MsmLaunchStats* stats,
+                   cudaStream_t tail_stream, cudaEvent_t ev_acc) {
+    return msm_buckets<FT>((const Affine<FT>*)d_bases, s, scratch, stream, (PT*)d_wsum, stats, tail_stream, ev_acc);
 }
 void bn254_g2_combine(const uint8_t* wsum_host, const MsmGeom& g, uint8_t* acc_xyzz) {
     PT acc; memcpy(&acc, acc_xyzz, sizeof acc);

@@ -9,7 +9,8 @@ struct MsmScratch; struct MsmLaunchStats; struct MsmSorted;
 // coordinate bytes (n8q or 2*n8q) of the group's field
 #define SB_DECL_GROUP(NAME) \
     /* async: bucket pipeline for one base set over sorted entries; d_wsum = device buffer of W XYZZ points */ \
-    int NAME##_buckets(const void* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream, void* d_wsum, MsmLaunchStats* stats); \
+    int NAME##_buckets(const void* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream, void* d_wsum, MsmLaunchStats* stats, \
+                       cudaStream_t tail_stream, cudaEvent_t ev_acc); \
     /* host: Horner over W window sums (host bytes) added into acc_xyzz (host XYZZ bytes, in/out) */ \
     void NAME##_combine(const uint8_t* wsum_host, const MsmGeom& g, uint8_t* acc_xyzz); \
     /* host: acc_xyzz += other */ \
