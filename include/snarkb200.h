@@ -104,6 +104,17 @@ uint32_t sb_groth16_partials_bytes(sb_ctx* ctx);
 int sb_groth16_finish(sb_ctx* ctx, uint64_t handle, const uint8_t* partials_all_ranks, int n_shards,
                       const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
 
+/* Host-only halves of the multi-GPU path (no context, no device needed): combine partials gathered from the ranks and
+ * assemble the proof (src/groth16_prove.js:103-132).  partial = extended-Jacobian X,Y,ZZ,ZZZ Montgomery bytes;
+ * Groth16 partial block = A | B1 | C | H (G1) | B2 (G2). */
+int sb_host_sum_partials(int curve, int group, const uint8_t* partials, int count, uint8_t* out_jacobian);
+int sb_host_partial_from_affine(int curve, int group, const uint8_t* affine, uint8_t* partial_out);
+uint32_t sb_host_partial_bytes(int curve, int group);
+int sb_host_groth16_finish(int curve, const uint8_t* vk_alpha1, const uint8_t* vk_beta1, const uint8_t* vk_beta2,
+                           const uint8_t* vk_delta1, const uint8_t* vk_delta2, const uint8_t* partials_all_ranks, int n_shards,
+                           const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
+void sb_shard_range(uint64_t total, int shard, int n_shards, uint64_t* first, uint64_t* count);
+
 /* Device-resident variants (inputs already in HBM): what bench.py's `value` times.  Pointers are device pointers
  * in this context's device; out is host memory. */
 int sb_msm_dev(sb_ctx* ctx, int group, const void* bases_dev, const void* scalars_dev, uint32_t scalar_bytes, uint64_t n, uint8_t* out);

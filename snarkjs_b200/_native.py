@@ -54,6 +54,11 @@ _SIGNATURES = {
     "sb_groth16_prove_shard": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_int, ctypes.c_int, vp]),
     "sb_groth16_partials_bytes": (u32, [vp]),
     "sb_groth16_finish": (ctypes.c_int, [vp, u64, vp, ctypes.c_int, vp, vp, vp]),
+    "sb_host_sum_partials": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp]),
+    "sb_host_partial_from_affine": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp]),
+    "sb_host_partial_bytes": (u32, [ctypes.c_int, ctypes.c_int]),
+    "sb_host_groth16_finish": (ctypes.c_int, [ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp]),
+    "sb_shard_range": (None, [u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "sb_msm_dev": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, u32, u64, vp]),
     "sb_ntt_fr_dev": (ctypes.c_int, [vp, vp, vp, u64, ctypes.c_int, ctypes.POINTER(vp)]),
     "sb_dev_alloc": (vp, [vp, u64]),

@@ -794,7 +794,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     return 0;
     };
     // MSMs (:84-101).  Shard = contiguous point range; shard 0 of 1 = everything.
-    auto range = [&](uint64_t total, uint64_t& lo, uint64_t& cnt) { uint64_t per = (total + n_shards - 1) / n_shards; lo = std::min(total, per * shard); cnt = std::min(total - lo, per); };
+    auto range = [&](uint64_t total, uint64_t& lo, uint64_t& cnt) { sb_shard_range(total, shard, n_shards, &lo, &cnt); };
     const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
     uint8_t* pA = partials; uint8_t* pB1 = pA + G1.xyzz_bytes; uint8_t* pC = pB1 + G1.xyzz_bytes; uint8_t* pH = pC + G1.xyzz_bytes; uint8_t* pB2 = pH + G1.xyzz_bytes;
     memset(partials, 0, 4 * G1.xyzz_bytes + G2.xyzz_bytes);
@@ -915,24 +915,31 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
 
 // host part: proof assembly, src/groth16_prove.js:103-132
 
+struct VkPoints { const uint8_t *alpha1, *beta1, *beta2, *delta1, *delta2; };
+static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& G2, const VkPoints& vk, const uint8_t* partials,
+                                 const uint8_t r[32], const uint8_t s[32], uint8_t* proof);
 static int groth16_assemble(sb_ctx* c, Groth16Key* k, const uint8_t* partials, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
-    const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
+    VkPoints vk{k->alpha1.data(), k->beta1.data(), k->beta2.data(), k->delta1.data(), k->delta2.data()};
+    return groth16_assemble_host(c->curve, c->g1, c->g2, vk, partials, r, s, proof);
+}
+static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& G2, const VkPoints& vk, const uint8_t* partials,
+                                 const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
     const uint32_t x1 = G1.xyzz_bytes, x2 = G2.xyzz_bytes;
     std::vector<uint8_t> A(partials, partials + x1), B1(partials + x1, partials + 2 * x1), C(partials + 2 * x1, partials + 3 * x1),
         H(partials + 3 * x1, partials + 4 * x1), B2(partials + 4 * x1, partials + 4 * x1 + x2);
     uint8_t rp[32], sp[32], rs[32], rsp[32];
-    if (c->curve == SB_BN254) { fr_from_mont_bytes<BnFr>(r, rp); fr_from_mont_bytes<BnFr>(s, sp); fr_neg_mul_bytes<BnFr>(r, s, rs); fr_from_mont_bytes<BnFr>(rs, rsp); }
+    if (curve == SB_BN254) { fr_from_mont_bytes<BnFr>(r, rp); fr_from_mont_bytes<BnFr>(s, sp); fr_neg_mul_bytes<BnFr>(r, s, rs); fr_from_mont_bytes<BnFr>(rs, rsp); }
     else { fr_from_mont_bytes<BlsFr>(r, rp); fr_from_mont_bytes<BlsFr>(s, sp); fr_neg_mul_bytes<BlsFr>(r, s, rs); fr_from_mont_bytes<BlsFr>(rs, rsp); }
     std::vector<uint8_t> t1(x1), t2(x2), d1(x1), d2(x2), pt(x1), pt2(x2);
-    G1.from_affine(k->delta1.data(), d1.data()); G2.from_affine(k->delta2.data(), d2.data());
+    G1.from_affine(vk.delta1, d1.data()); G2.from_affine(vk.delta2, d2.data());
     // pi_a = A + alpha1 + r*delta1
-    G1.from_affine(k->alpha1.data(), pt.data()); G1.add(A.data(), pt.data());
+    G1.from_affine(vk.alpha1, pt.data()); G1.add(A.data(), pt.data());
     G1.times(d1.data(), rp, 32, t1.data()); G1.add(A.data(), t1.data());
     // pi_b = B2 + beta2 + s*delta2
-    G2.from_affine(k->beta2.data(), pt2.data()); G2.add(B2.data(), pt2.data());
+    G2.from_affine(vk.beta2, pt2.data()); G2.add(B2.data(), pt2.data());
     G2.times(d2.data(), sp, 32, t2.data()); G2.add(B2.data(), t2.data());
     // pib1 = B1 + beta1 + s*delta1
-    G1.from_affine(k->beta1.data(), pt.data()); G1.add(B1.data(), pt.data());
+    G1.from_affine(vk.beta1, pt.data()); G1.add(B1.data(), pt.data());
     G1.times(d1.data(), sp, 32, t1.data()); G1.add(B1.data(), t1.data());
     // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1
     G1.add(C.data(), H.data());
@@ -973,6 +980,51 @@ int sb_groth16_finish(sb_ctx* c, uint64_t h, const uint8_t* all, int n_shards, c
         G2.add(acc.data() + 4 * x1, p + 4 * x1);
     }
     return groth16_assemble(c, k, acc.data(), r, s, proof);
+}
+
+// ---- host-only helpers (no context, no device): the combine/assembly half of the multi-GPU path, testable on CPU
+static void host_ops(int curve, GroupOps& g1, GroupOps& g2) {
+    if (curve == SB_BN254) { g1 = SB_GROUP_OPS(bn254_g1, 64); g2 = SB_GROUP_OPS(bn254_g2, 128); }
+    else { g1 = SB_GROUP_OPS(bls12381_g1, 96); g2 = SB_GROUP_OPS(bls12381_g2, 192); }
+}
+int sb_host_sum_partials(int curve, int group, const uint8_t* partials, int count, uint8_t* out_jacobian) {
+    if ((curve != SB_BN254 && curve != SB_BLS12_381) || (group != SB_G1 && group != SB_G2) || count < 0) return SB_ERR_ARG;
+    GroupOps g1, g2; host_ops(curve, g1, g2);
+    const GroupOps& G = group == SB_G1 ? g1 : g2;
+    std::vector<uint8_t> acc(G.xyzz_bytes, 0);
+    for (int i = 0; i < count; i++) G.add(acc.data(), partials + (size_t)i * G.xyzz_bytes);
+    G.to_jacobian(acc.data(), out_jacobian);
+    return 0;
+}
+int sb_host_partial_from_affine(int curve, int group, const uint8_t* affine, uint8_t* partial_out) {
+    if ((curve != SB_BN254 && curve != SB_BLS12_381) || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
+    GroupOps g1, g2; host_ops(curve, g1, g2);
+    (group == SB_G1 ? g1 : g2).from_affine(affine, partial_out);
+    return 0;
+}
+uint32_t sb_host_partial_bytes(int curve, int group) {
+    GroupOps g1, g2; if (curve != SB_BN254 && curve != SB_BLS12_381) return 0; host_ops(curve, g1, g2);
+    return group == SB_G1 ? g1.xyzz_bytes : g2.xyzz_bytes;
+}
+int sb_host_groth16_finish(int curve, const uint8_t* vk_alpha1, const uint8_t* vk_beta1, const uint8_t* vk_beta2,
+                           const uint8_t* vk_delta1, const uint8_t* vk_delta2, const uint8_t* partials_all_ranks, int n_shards,
+                           const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out) {
+    if ((curve != SB_BN254 && curve != SB_BLS12_381) || n_shards < 1) return SB_ERR_ARG;
+    GroupOps G1, G2; host_ops(curve, G1, G2);
+    const uint32_t x1 = G1.xyzz_bytes, pb = 4 * G1.xyzz_bytes + G2.xyzz_bytes;
+    std::vector<uint8_t> acc(pb, 0);
+    for (int i = 0; i < n_shards; i++) {
+        const uint8_t* p = partials_all_ranks + (size_t)i * pb;
+        for (int j = 0; j < 4; j++) G1.add(acc.data() + j * x1, p + j * x1);
+        G2.add(acc.data() + 4 * x1, p + 4 * x1);
+    }
+    VkPoints vk{vk_alpha1, vk_beta1, vk_beta2, vk_delta1, vk_delta2};
+    return groth16_assemble_host(curve, G1, G2, vk, acc.data(), r, s, proof_affine_out);
+}
+// point range of shard `shard` of `n_shards` over `total` points (the split sb_groth16_prove_shard uses)
+void sb_shard_range(uint64_t total, int shard, int n_shards, uint64_t* first, uint64_t* count) {
+    uint64_t per = (total + n_shards - 1) / n_shards, lo = std::min(total, per * (uint64_t)shard);
+    *first = lo; *count = std::min(total - lo, per);
 }
 
 int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
