@@ -29,13 +29,17 @@ template <class P> struct Fp2 {
     SB_HD static Fp2 neg(const Fp2& x) { Fp2 r; r.a = B::neg(x.a); r.b = B::neg(x.b); return r; }
     SB_HD static Fp2 cneg(const Fp2& x, bool f) { Fp2 r; r.a = B::cneg(x.a, f); r.b = B::cneg(x.b, f); return r; }
     // Karatsuba, 3 base multiplies
-    SB_HD_NOINLINE static Fp2 mul(const Fp2& x, const Fp2& y) {
+    SB_HD_NOINLINE static Fp2 mul(const Fp2& x, const Fp2& y) { return mul_i(x, y); }
+    SB_HD_NOINLINE static Fp2 sqr(const Fp2& x) { return sqr_i(x); }
+    // force-inlined variants for the hot bucket-accumulation loop (everything else calls the out-of-line ones to keep
+    // code size and compile time down)
+    SB_HD static Fp2 mul_i(const Fp2& x, const Fp2& y) {
         B A = B::mul(x.a, y.a), Bb = B::mul(x.b, y.b);
         B C = B::mul(B::add(x.a, x.b), B::add(y.a, y.b));
         Fp2 r; r.a = B::sub(A, Bb); r.b = B::sub(B::sub(C, A), Bb); return r;
     }
     // complex squaring, 2 base multiplies
-    SB_HD_NOINLINE static Fp2 sqr(const Fp2& x) {
+    SB_HD static Fp2 sqr_i(const Fp2& x) {
         B AB = B::mul(x.a, x.b);
         Fp2 r; r.a = B::mul(B::add(x.a, x.b), B::sub(x.a, x.b)); r.b = B::dbl(AB); return r;
     }
@@ -79,17 +83,17 @@ template <class F> struct XYZZ {
     // acc += (qx, qy) affine, q not infinity (madd-2008-s), `one` = Montgomery 1.
     SB_HD void add_affine(const F& qx, const F& qy, const F& one) {
         if (is_inf()) { x = qx; y = qy; zz = one; zzz = one; return; }
-        F U2 = F::mul(qx, zz), S2 = F::mul(qy, zzz);
+        F U2 = F::mul_i(qx, zz), S2 = F::mul_i(qy, zzz);
         F Pp = F::sub(U2, x), R = F::sub(S2, y);
         if (Pp.is_zero()) {            // same x: doubling or cancellation (reference 6620-6640 special cases)
             if (R.is_zero()) *this = dbl_affine(qx, qy, one);
             else *this = inf();
             return;
         }
-        F PP = F::sqr(Pp), PPP = F::mul(Pp, PP), Q = F::mul(x, PP);
-        F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-        F Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(y, PPP));
-        x = X3; y = Y3; zz = F::mul(zz, PP); zzz = F::mul(zzz, PPP);
+        F PP = F::sqr_i(Pp), PPP = F::mul_i(Pp, PP), Q = F::mul_i(x, PP);
+        F X3 = F::sub(F::sub(F::sqr_i(R), PPP), F::dbl(Q));
+        F Y3 = F::sub(F::mul_i(R, F::sub(Q, X3)), F::mul_i(y, PPP));
+        x = X3; y = Y3; zz = F::mul_i(zz, PP); zzz = F::mul_i(zzz, PPP);
     }
     // acc += q   (add-2008-s)
     SB_HD void add(const XYZZ& q) {

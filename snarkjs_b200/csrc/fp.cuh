@@ -252,6 +252,8 @@ _Pragma("unroll")
 #endif
     }
     SB_HD static Fp sqr(const Fp& a) { return mul(a, a); }
+    SB_HD static Fp mul_i(const Fp& a, const Fp& b) { return mul(a, b); }
+    SB_HD static Fp sqr_i(const Fp& a) { return mul(a, a); }
     SB_HD static Fp to_mont(const Fp& a) { return mul(a, r2()); }
 
 #ifndef __CUDA_ARCH__

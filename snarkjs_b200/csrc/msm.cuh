@@ -375,11 +375,17 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
         if (prof) cudaEventRecord(stats->ev[stats->used], stream);
         {
             const unsigned grid = (unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-            switch (g_msm_tuning[0]) {   // experimental occupancy variants (sb_set_tuning(0, minBlocksPerSM))
-            case 5: k_accumulate<F, 5><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
-            case 6: k_accumulate<F, 6><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
-            case 8: k_accumulate<F, 8><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
-            default: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+            // occupancy variants (sb_set_tuning(0, minBlocksPerSM)): base-field groups run best at 4 CTAs/SM (124 regs);
+            // extension-field groups (accumulator = 64-96 registers) have their own variants
+            constexpr bool ext = sizeof(F) > 48 && (sizeof(F) % 64 == 0 || sizeof(F) == 96);
+            if constexpr (ext) {
+                switch (g_msm_tuning[0]) {
+                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
+                }
+            } else {
+                k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);
             }
             launches++;
         }
