@@ -153,7 +153,7 @@ def run_b200(args):
     peak_modmul = curve.lib.sb_calibrate(curve.handle, 1) if rank == 0 else 0.0
     t0 = time.perf_counter()
     zkey = synth.synth_groth16_zkey(curve, L, seed=1)
-    pk = groth16.ProvingKey(zkey, curve=curve)
+    pk = groth16.ProvingKey(zkey, curve=curve, shard=rank, n_shards=world)
     t_setup = time.perf_counter() - t0
     wit_np = synth.chain_witness(curve.r, L)
     wit = torch.from_numpy(wit_np.copy()).pin_memory()           # pinned host witness: the e2e input

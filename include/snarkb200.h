@@ -85,6 +85,9 @@ int sb_fr_root(sb_ctx* ctx, int what, uint8_t out[32]);
  * pi_c (2*n8q), Montgomery.  public signals are witness[1..nPublic]. */
 int sb_groth16_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handle);
 int sb_groth16_load_file(sb_ctx* ctx, const char* zkey_path, uint64_t* handle);
+/* multi-GPU variant: this rank keeps (and builds window tables for) only its point-range shard of the five base sets;
+ * the handle then serves sb_groth16_prove_shard(shard, n_shards) only. */
+int sb_groth16_load_sharded(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, int shard, int n_shards, uint64_t* handle);
 int sb_groth16_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size);
 int sb_groth16_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness,
                      const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "sb_qap_join_abc": (ctypes.c_int, [vp, vp, vp, vp, u64, vp]),
     "sb_fr_root": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "sb_groth16_load": (ctypes.c_int, [vp, vp, u64, ctypes.POINTER(u64)]),
+    "sb_groth16_load_sharded": (ctypes.c_int, [vp, vp, u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u64)]),
     "sb_groth16_load_file": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.POINTER(u64)]),
     "sb_groth16_info": (ctypes.c_int, [vp, u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "sb_groth16_prove": (ctypes.c_int, [vp, u64, vp, u64, vp, vp, vp]),

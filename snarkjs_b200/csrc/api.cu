@@ -56,6 +56,8 @@ struct Groth16Key {
     void *dA = nullptr, *dB1 = nullptr, *dB2 = nullptr, *dC = nullptr, *dH = nullptr;   // bases (C padded to nVars)
     void *tA = nullptr, *tB1 = nullptr, *tB2 = nullptr, *tC = nullptr, *tH = nullptr;   // precomputed window tables
     MsmGeom gpW{}, gpH{};                                                                // their geometry (precomp != 0 when built)
+    // sharded load (multi-GPU): only the point ranges [wlo, wlo+wcnt) of A/B1/B2/C and [hlo, hlo+hcnt) of H are resident
+    int shard = 0, n_shards = 1; uint64_t wlo = 0, wcnt = 0, hlo = 0, hcnt = 0;
     uint64_t* d_rowptr = nullptr; uint32_t* d_sig = nullptr; void* d_coef = nullptr; uint64_t nCoef = 0;
     // device work buffers
     void *dW = nullptr, *dA_T = nullptr, *dB_T = nullptr, *dC_T = nullptr, *dTmp = nullptr, *dWsum = nullptr;
@@ -648,8 +650,8 @@ int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { if
 int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
 
 // ---------------------------------------------------------------------------------------------------- Groth16
-int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) {
-    if (!c || !z || !handle) return SB_ERR_ARG;
+static int groth16_load_impl(sb_ctx* c, const uint8_t* z, uint64_t zlen, int shard, int n_shards, uint64_t* handle) {
+    if (!c || !z || !handle || n_shards < 1 || shard < 0 || shard >= n_shards) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     std::map<uint32_t, Section> secs;
     int rc = parse_binfile(c, z, zlen, "zkey", 2, secs); if (rc) return rc;
@@ -704,16 +706,22 @@ int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle
         e = cudaMalloc(d, alloc ? alloc : 16); if (e != cudaSuccess) return;
         if (bytes) e = cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice);
     };
-    up(&k->dA, z + secs[5].pos, nv * sG1, nv * sG1);
-    up(&k->dB1, z + secs[6].pos, nv * sG1, nv * sG1);
-    up(&k->dB2, z + secs[7].pos, nv * sG2, nv * sG2);
+    k->shard = shard; k->n_shards = n_shards;
+    sb_shard_range(nv, shard, n_shards, &k->wlo, &k->wcnt);
+    sb_shard_range(n, shard, n_shards, &k->hlo, &k->hcnt);
+    const uint64_t wlo = k->wlo, wcnt = k->wcnt, hlo = k->hlo, hcnt = k->hcnt;
+    up(&k->dA, z + secs[5].pos + wlo * sG1, wcnt * sG1, wcnt * sG1);
+    up(&k->dB1, z + secs[6].pos + wlo * sG1, wcnt * sG1, wcnt * sG1);
+    up(&k->dB2, z + secs[7].pos + wlo * sG2, wcnt * sG2, wcnt * sG2);
     // C bases are indexed by signal - (nPublic+1): pad so that one sorted digit list of the witness serves A, B1, B2 and C
     if (e == cudaSuccess) {
-        e = cudaMalloc(&k->dC, nv * sG1);
-        if (e == cudaSuccess) e = cudaMemset(k->dC, 0, (size_t)(k->nPublic + 1) * sG1);
-        if (e == cudaSuccess && secs[8].len) e = cudaMemcpy((uint8_t*)k->dC + (size_t)(k->nPublic + 1) * sG1, z + secs[8].pos, secs[8].len, cudaMemcpyHostToDevice);
+        const uint64_t np1 = (uint64_t)k->nPublic + 1;
+        e = cudaMalloc(&k->dC, wcnt ? wcnt * sG1 : 16);
+        if (e == cudaSuccess && wcnt) e = cudaMemset(k->dC, 0, wcnt * sG1);
+        const uint64_t g0 = std::max(wlo, np1), g1 = wlo + wcnt;
+        if (e == cudaSuccess && g1 > g0) e = cudaMemcpy((uint8_t*)k->dC + (g0 - wlo) * sG1, z + secs[8].pos + (g0 - np1) * sG1, (g1 - g0) * sG1, cudaMemcpyHostToDevice);
     }
-    up(&k->dH, z + secs[9].pos, n * sG1, n * sG1);
+    up(&k->dH, z + secs[9].pos + hlo * sG1, hcnt * sG1, hcnt * sG1);
     up((void**)&k->d_rowptr, rowptr.data(), rowptr.size() * 8, rowptr.size() * 8);
     up((void**)&k->d_sig, sig.data(), (size_t)ncoef * 4, (size_t)ncoef * 4);
     up(&k->d_coef, coef.data(), (size_t)ncoef * 32, (size_t)ncoef * 32);
@@ -721,17 +729,22 @@ int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle
     up(&k->dA_T, nullptr, 0, n * 32); up(&k->dB_T, nullptr, 0, n * 32); up(&k->dC_T, nullptr, 0, n * 32); up(&k->dTmp, nullptr, 0, n * 32);
     up(&k->dWsum, nullptr, 0, 8 * 80 * 4 * 96);
     if (e != cudaSuccess) { free_key(k); return cuda_fail(c, e, "sb_groth16_load upload"); }
-    if (want_precomp(c, nv) && want_precomp(c, n)) {
-        int rc2 = build_table(c, c->g1, k->dA, nv, &k->tA, &k->gpW);
-        if (!rc2) rc2 = build_table(c, c->g1, k->dB1, nv, &k->tB1, &k->gpW);
-        if (!rc2) rc2 = build_table(c, c->g2, k->dB2, nv, &k->tB2, &k->gpW);
-        if (!rc2) rc2 = build_table(c, c->g1, k->dC, nv, &k->tC, &k->gpW);
-        if (!rc2) rc2 = build_table(c, c->g1, k->dH, n, &k->tH, &k->gpH);
+    if (want_precomp(c, wcnt) && want_precomp(c, hcnt)) {
+        int rc2 = build_table(c, c->g1, k->dA, wcnt, &k->tA, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g1, k->dB1, wcnt, &k->tB1, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g2, k->dB2, wcnt, &k->tB2, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g1, k->dC, wcnt, &k->tC, &k->gpW);
+        if (!rc2) rc2 = build_table(c, c->g1, k->dH, hcnt, &k->tH, &k->gpH);
         if (rc2) { free_key(k); return rc2; }
     }
     c->keys.push_back(k);
     *handle = c->keys.size();
     return 0;
+}
+
+int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) { return groth16_load_impl(c, z, zlen, 0, 1, handle); }
+int sb_groth16_load_sharded(sb_ctx* c, const uint8_t* z, uint64_t zlen, int shard, int n_shards, uint64_t* handle) {
+    return groth16_load_impl(c, z, zlen, shard, n_shards, handle);
 }
 
 int sb_groth16_load_file(sb_ctx* c, const char* path, uint64_t* handle) {
@@ -801,6 +814,10 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     static const uint64_t MAXC = 1ull << 23;
     uint64_t wlo, wcnt; range(nv, wlo, wcnt);
     uint64_t hlo, hcnt; range(n, hlo, hcnt);
+    // a key loaded with sb_groth16_load_sharded only holds its own ranges: local indexing
+    const bool local = k->n_shards > 1;
+    if (local && (shard != k->shard || n_shards != k->n_shards)) return fail(c, SB_ERR_ARG, "proving key was loaded for a different shard");
+    const uint64_t wb = local ? 0 : wlo, hb = local ? 0 : hlo;   // base-set index of this call's first point
     if (wcnt <= MAXC && hcnt <= MAXC && wcnt > 0 && hcnt > 0 && c->pinned) {
         // Overlapped pipeline: the witness is sorted once (A, B1, B2 and C all multiply it, :84-97); the four bucket
         // pipelines run on their own streams so that the latency-bound tails (fold cascade, bucket reduction) of one
@@ -814,7 +831,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         cudaStream_t sN = serial ? s0 : c->aux[5];
         MsmGeom gw = msm_geometry(wcnt, 32, c->fr_bits), gh = msm_geometry(hcnt, 32, c->fr_bits);
         const bool pre = k->tA != nullptr;
-        if (pre) { gw = k->gpW; gw.first = wlo; gh = k->gpH; gh.first = hlo; }
+        if (pre) { gw = k->gpW; gw.first = wb; gh = k->gpH; gh.first = hb; }
         const size_t w1 = (size_t)gw.windows() * G1.xyzz_bytes, w2 = (size_t)gw.windows() * G2.xyzz_bytes, wh = (size_t)gh.windows() * G1.xyzz_bytes;
         if (3 * w1 + w2 + wh + 64 > 256 * 1024 || 3 * w1 + w2 + wh > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
         uint8_t* dws = (uint8_t*)k->dWsum; uint8_t* hws = c->pinned;
@@ -839,11 +856,11 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
         tick(c, 2);
         struct Job { const GroupOps* G; const void* bases; size_t off; size_t len; uint8_t* dst; int tag; const MsmSorted* srt; const MsmGeom* g; };
-        Job jobs[5] = {{&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wlo * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2, &sw, &gw},
-                       {&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wlo * G1.aff_bytes), 0, w1, pA, SB_G1, &sw, &gw},
-                       {&G1, pre ? k->tB1 : (const void*)((const uint8_t*)k->dB1 + wlo * G1.aff_bytes), w1, w1, pB1, SB_G1, &sw, &gw},
-                       {&G1, pre ? k->tC : (const void*)((const uint8_t*)k->dC + wlo * G1.aff_bytes), 2 * w1, w1, pC, SB_G1, &sw, &gw},
-                       {&G1, pre ? k->tH : (const void*)((const uint8_t*)k->dH + hlo * G1.aff_bytes), 3 * w1 + w2, wh, pH, SB_G1, &sh, &gh}};
+        Job jobs[5] = {{&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wb * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2, &sw, &gw},
+                       {&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wb * G1.aff_bytes), 0, w1, pA, SB_G1, &sw, &gw},
+                       {&G1, pre ? k->tB1 : (const void*)((const uint8_t*)k->dB1 + wb * G1.aff_bytes), w1, w1, pB1, SB_G1, &sw, &gw},
+                       {&G1, pre ? k->tC : (const void*)((const uint8_t*)k->dC + wb * G1.aff_bytes), 2 * w1, w1, pC, SB_G1, &sw, &gw},
+                       {&G1, pre ? k->tH : (const void*)((const uint8_t*)k->dH + hb * G1.aff_bytes), 3 * w1 + w2, wh, pH, SB_G1, &sh, &gh}};
         for (int i = 0; i < 5; i++) {
             cudaStream_t st = serial ? s0 : c->aux[i];
             if (i == 4 && sN != s0) CU(c, cudaStreamWaitEvent(s0, c->pev[1], 0));   // H needs the NTT chain
@@ -878,10 +895,10 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     rc = run_qap_ntt(); if (rc) return rc;
     tick(c, 2);
     for (uint64_t off = 0; off < wcnt; off += MAXC) {
-        uint64_t cn = std::min(MAXC, wcnt - off), base = wlo + off;
+        uint64_t cn = std::min(MAXC, wcnt - off), base = wb + off;
         MsmGeom g = msm_geometry(cn, 32, c->fr_bits);
         MsmSorted s;
-        rc = msm_sort_entries((const uint8_t*)k->dW + base * 32, 32, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
+        rc = msm_sort_entries((const uint8_t*)k->dW + (wlo + off) * 32, 32, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
         uint8_t* ws = (uint8_t*)k->dWsum;
         size_t w1 = (size_t)g.W * G1.xyzz_bytes, w2 = (size_t)g.W * G2.xyzz_bytes;
@@ -902,7 +919,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     }
     tick(c, 3);
     if (hcnt) {
-        rc = msm_dev_accumulate(c, G1, (const uint8_t*)k->dH + hlo * G1.aff_bytes, (const uint8_t*)tmp + hlo * 32, 32, hcnt, pH);
+        rc = msm_dev_accumulate(c, G1, (const uint8_t*)k->dH + hb * G1.aff_bytes, (const uint8_t*)tmp + hlo * 32, 32, hcnt, pH);
         if (rc) return rc;
     }
     }
@@ -954,6 +971,7 @@ static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& 
 
 int sb_groth16_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    if (k->n_shards > 1) return fail(c, SB_ERR_ARG, "proving key was loaded sharded: use sb_groth16_prove_shard + sb_groth16_finish");
     std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
     int rc = groth16_device(c, k, witness, n_witness, 0, 1, partials.data()); if (rc) return rc;
     return groth16_assemble(c, k, partials.data(), r, s, proof);

@@ -56,7 +56,7 @@ __host__ inline MsmGeom msm_choose(uint64_t n, uint32_t scalar_bytes, int fr_bit
 // (a few dozen entries) also keep the per-thread head partials short-run, i.e. on the parallel k_fold_short path.
 __host__ inline MsmGeom msm_geometry_precomp(uint64_t n_set, uint32_t scalar_bytes, int fr_bits = 254) {
     int l2 = 0; while ((1ull << (l2 + 1)) <= n_set) l2++;
-    int cmax = l2 + 1; if (cmax > 22) cmax = 22; if (cmax < 8) cmax = 8;
+    int cmax = l2; if (cmax > 22) cmax = 22; if (cmax < 8) cmax = 8;   // 2^(c-1) <= n/2: the bucket pass (1.3 ns/bucket) stays below ~1/3 of the accumulation (0.16 ns/entry)
     int c = 8;
     for (int cc = cmax; cc >= 8; cc--) {
         int weff = (fr_bits + 1 + cc - 1) / cc, top = fr_bits + 1 - (weff - 1) * cc;

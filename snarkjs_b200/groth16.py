@@ -105,14 +105,17 @@ def proof_to_object(curve: Curve, affine: bytes) -> dict:
 class ProvingKey:
     """A Groth16 zkey registered on one device (bases + CSR coefficients resident in HBM)."""
 
-    def __init__(self, zkey: bytes, curve: Curve | None = None, device: int = 0):
+    def __init__(self, zkey: bytes, curve: Curve | None = None, device: int = 0, shard: int = 0, n_shards: int = 1):
         zkey = bytes(zkey)
         self.header = read_zkey_header_groth16(zkey)
         self.curve = curve or getCurveFromQ(self.header["q"], device)
         self._own_curve = curve is None
         h = ctypes.c_uint64()
         buf = np.frombuffer(zkey, np.uint8)
-        self.curve.check(self.curve.lib.sb_groth16_load(self.curve.handle, _ptr(buf), buf.size, ctypes.byref(h)))
+        if n_shards > 1:   # multi-GPU: keep only this rank's point range of every base set (and its window tables)
+            self.curve.check(self.curve.lib.sb_groth16_load_sharded(self.curve.handle, _ptr(buf), buf.size, shard, n_shards, ctypes.byref(h)))
+        else:
+            self.curve.check(self.curve.lib.sb_groth16_load(self.curve.handle, _ptr(buf), buf.size, ctypes.byref(h)))
         self.handle = h.value
         self.nVars, self.nPublic, self.domainSize = self.header["nVars"], self.header["nPublic"], self.header["domainSize"]
 

@@ -359,3 +359,25 @@ def test_msm_plain_vs_table_mode(bn):
     # sub-range of a registered table
     c = bn.G2.multiExpRegistered(h1, sc[100 * 32:5100 * 32], first=100, n=5000)
     assert bn.G2.toAffine(c).tobytes() == O.g_to_affine(BN, 2, O.multiexp_affine(BN, 2, bases[100 * 128:5100 * 128], sc[100 * 32:5100 * 32]))
+
+
+def test_groth16_sharded_keys_match_unsharded(bn):
+    """Multi-GPU layout on one device: three proving keys each holding one point-range shard (with their own window
+    tables); the gathered partials finish to the same proof as the unsharded key; a sharded key refuses other shards."""
+    from snarkjs_b200 import groth16, synth, SbError
+    L = 15
+    zkey = synth.synth_groth16_zkey(bn, L, seed=9)
+    w = synth.chain_witness(bn.r, L)
+    ci = O.CURVES[BN]
+    r, s = ci.fr_to_mont(4242), ci.fr_to_mont(2424)
+    full = groth16.ProvingKey(zkey, curve=bn)
+    want = full.prove_raw(w, r, s)
+    keys = [groth16.ProvingKey(zkey, curve=bn, shard=i, n_shards=3) for i in range(3)]
+    parts = np.concatenate([keys[i].prove_shard(w, i, 3) for i in range(3)])
+    assert keys[0].finish(parts, 3, r, s) == want
+    with pytest.raises(SbError, match="different shard"):
+        keys[0].prove_shard(w, 1, 3)
+    with pytest.raises(SbError, match="loaded sharded"):
+        keys[0].prove_raw(w, r, s)
+    for k in keys + [full]:
+        k.release()
