@@ -17,7 +17,7 @@ template <class P> struct Fp2 {
     B a, b;
     SB_HD static Fp2 one() { Fp2 r; r.a = B::one(); r.b = B::zero(); return r; }
     SB_HD static Fp2 inv(const Fp2& x) {   // (a - bu)/(a^2 + b^2)
-        B t = B::inv(B::add(B::sqr(x.a), B::sqr(x.b)));
+        B t = B::inv_binary(B::add(B::sqr(x.a), B::sqr(x.b)));
         Fp2 r; r.a = B::mul(x.a, t); r.b = B::neg(B::mul(x.b, t)); return r;
     }
     SB_HD static Fp2 zero() { Fp2 r; r.a = B::zero(); r.b = B::zero(); return r; }

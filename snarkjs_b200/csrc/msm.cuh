@@ -97,6 +97,10 @@ template <class T> __device__ __forceinline__ T load_vec(const T* src) {
     return v;
 }
 
+// field inversion on the device: binary (Kaliski) for Fp, norm + binary for Fp2
+template <class P> __device__ __forceinline__ Fp<P> PairInvF(const Fp<P>& a) { return Fp<P>::inv_binary(a); }
+template <class P> __device__ __forceinline__ Fp2<P> PairInvF(const Fp2<P>& a) { return Fp2<P>::inv(a); }
+
 // ------------------------------------------------------------------------------------------------
 // level 0: affine bases gathered through the sorted (key, val) list
 // ------------------------------------------------------------------------------------------------
@@ -115,7 +119,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ k
     uint32_t cur = keys[lo];
     bool first = true;
     for (uint64_t e = lo; e < hi; e++) {
-        uint32_t k = keys[e], v = vals[e];
+        uint32_t k = keys[e], v = vals ? vals[e] : (uint32_t)e;
         if (k != cur) {
             if (first) { store_vec(heads + t, acc); head_keys[t] = cur; first = false; }
             else store_vec(buckets + cur, acc);
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(128) k_precompute(const Affine<F>* __restrict_
         for (int j = 0; j < c; j++) p = XYZZ<F>::dbl(p);
         Affine<F> o;
         if (p.is_inf()) { o.x = F::zero(); o.y = F::zero(); }
-        else { F t = F::inv(F::mul(p.zz, p.zzz)); o.x = F::mul(p.x, F::mul(t, p.zzz)); o.y = F::mul(p.y, F::mul(t, p.zz)); p.x = o.x; p.y = o.y; p.zz = F::one(); p.zzz = F::one(); }
+        else { F t = PairInvF(F::mul(p.zz, p.zzz)); o.x = F::mul(p.x, F::mul(t, p.zzz)); o.y = F::mul(p.y, F::mul(t, p.zz)); p.x = o.x; p.y = o.y; p.zz = F::one(); p.zzz = F::one(); }
         store_vec(table + (uint64_t)w * n + i, o);
     }
 }
@@ -303,9 +307,13 @@ __global__ void __launch_bounds__(128) k_gen_points(Affine<F> g, uint64_t seed, 
     }
     Affine<F> a;
     if (r.is_inf()) { a.x = F::zero(); a.y = F::zero(); }
-    else { F t = F::inv(F::mul(r.zz, r.zzz)); a.x = F::mul(r.x, F::mul(t, r.zzz)); a.y = F::mul(r.y, F::mul(t, r.zz)); }
+    else { F t = PairInvF(F::mul(r.zz, r.zzz)); a.x = F::mul(r.x, F::mul(t, r.zzz)); a.y = F::mul(r.y, F::mul(t, r.zz)); }
     store_vec(out + i, a);
 }
+
+}  // namespace sb
+#include "msm_pair.cuh"
+namespace sb {
 
 // ------------------------------------------------------------------------------------------------
 // Device scratch (grow-only) and the two halves of the pipeline.
@@ -334,6 +342,12 @@ struct MsmSorted {
     uint64_t n = 0, total = 0; MsmGeom g{};
 };
 
+// msm_sort.cu: helpers of the pairing rounds (non-template part)
+size_t msm_pair_scan_tmp_bytes(uint32_t NB);
+int msm_pair_offsets(const uint32_t* keys, const uint64_t* counts, uint32_t NB, uint32_t* off, cudaStream_t stream);
+int msm_pair_next_offsets(const uint32_t* off_in, uint32_t NB, uint32_t* sizes, uint32_t* off_out, void* tmp, size_t tmp_bytes, cudaStream_t stream);
+int msm_pair_counts(const uint32_t* off, uint32_t NB, uint64_t* counts, cudaStream_t stream);
+
 // msm_sort.cu: digits + radix sort + valid count.  d_scalars is a device pointer.
 int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmGeom g, MsmScratch& scratch,
                      cudaStream_t stream, MsmSorted* out, MsmLaunchStats* stats);
@@ -343,8 +357,85 @@ int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmG
 // (fold, bucket reduction, window sum) on `tail_stream` after `ev_acc` (recorded here): with a higher-priority tail
 // stream the tail of one MSM slips into the SM slots freed by the next MSM's accumulation instead of queueing behind it.
 template <class F>
+int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratch, size_t scratch_off, cudaStream_t stream,
+                     XYZZ<F>* d_wsum, MsmLaunchStats* stats, cudaStream_t tail_stream, cudaEvent_t ev_acc);
+
+// Entry: optional batched-affine pairing rounds (msm_pair.cuh) shrink the entry list first, then the segmented XYZZ
+// pipeline runs on what is left.  EXPERIMENTAL, off by default (enable with sb_set_tuning(4, 2), cap the rounds with
+// sb_set_tuning(5, R)): measured on B200 at 2^20 the rounds run the integer pipe at 40-60 % (scan + shared inversion +
+// two gather passes) against 93 % / 71 % for the XYZZ accumulation, which cancels the 6-vs-10 modmul advantage
+// (G1 3.7 ms vs 3.4 ms per MSM, G2 11.6 ms vs 11.8 ms; profiles/README.md).
+template <class F>
 int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream,
                 XYZZ<F>* d_wsum, MsmLaunchStats* stats, cudaStream_t tail_stream = nullptr, cudaEvent_t ev_acc = nullptr) {
+    const MsmGeom g = s.g;
+    const uint64_t NBl = (uint64_t)g.windows() * g.B;
+    const double avg = NBl ? (double)s.total / (double)NBl : 0.0;
+    if (g_msm_tuning[4] != 2 || avg < 4.0 || NBl >= (1ull << 31) || s.total >= (1ull << 31))
+        return msm_buckets_impl<F>(d_bases, s, scratch, 0, stream, d_wsum, stats, tail_stream, ev_acc);
+    const uint32_t NB = (uint32_t)NBl;
+    int R = 1; while ((1u << R) < 2.0 * avg && R < 8) R++;
+    if (g_msm_tuning[5] > 0 && g_msm_tuning[5] < R) R = g_msm_tuning[5];   // cap on the number of pairing rounds (experiments)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const uint64_t ub1 = (s.total + NB + 1) / 2;
+    const size_t scan_tmp = msm_pair_scan_tmp_bytes(NB);
+    const uint64_t pthreads = ((ub1 + PAIR_K - 1) / PAIR_K + PAIR_THREADS - 1) / PAIR_THREADS * PAIR_THREADS;
+    size_t o_offA = 0, o_offB = o_offA + al((size_t)(NB + 1) * 4), o_sizes = o_offB + al((size_t)(NB + 1) * 4);
+    size_t o_tmp = o_sizes + al((size_t)(NB + 1) * 4), o_cnt = o_tmp + al(scan_tmp);
+    size_t o_PA = o_cnt + 256, o_PB = o_PA + al(ub1 * sizeof(Affine<F>)), o_KA = o_PB + al(ub1 * sizeof(Affine<F>));
+    size_t o_KB = o_KA + al(ub1 * 4), o_L = o_KB + al(ub1 * 4), o_rest = o_L + al(pthreads * PAIR_K * sizeof(F));
+    // size the rest (buckets, heads, partials) for the list that survives the rounds
+    uint64_t ub = s.total; for (int r = 0; r < R; r++) ub = (ub + NB + 1) / 2;
+    MsmSorted s2 = s; s2.total = ub; s2.vals = nullptr;
+    // first call sizes the whole scratch: probe the tail's requirement with a dry computation (same formula as impl)
+    {
+        const uint64_t heads0 = (ub + MSM_SEG - 1) / MSM_SEG, heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
+        const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
+        const uint32_t ctas_per_window = (g.B / L + 127) / 128;
+        size_t need = al(NBl * sizeof(XYZZ<F>)) + al(heads0 * sizeof(XYZZ<F>)) + al(heads0 * 4) + al(heads1 * sizeof(XYZZ<F>)) + al(heads1 * 4) +
+                      al(heads0 * 4) + al((size_t)g.windows() * ctas_per_window * sizeof(XYZZ<F>));
+        need += need / 8 + (1u << 20);   // margin: the impl must never grow (= reallocate) the scratch the rounds are using
+        if (!scratch.get(o_rest + need)) return (int)cudaErrorMemoryAllocation;
+    }
+    uint8_t* base = (uint8_t*)scratch.p;
+    uint32_t* offA = (uint32_t*)(base + o_offA); uint32_t* offB = (uint32_t*)(base + o_offB); uint32_t* sizes = (uint32_t*)(base + o_sizes);
+    uint64_t* counts2 = (uint64_t*)(base + o_cnt);
+    Affine<F>* P[2] = {(Affine<F>*)(base + o_PA), (Affine<F>*)(base + o_PB)};
+    uint32_t* K[2] = {(uint32_t*)(base + o_KA), (uint32_t*)(base + o_KB)};
+    F* Ls = (F*)(base + o_L);
+    int launches = 0;
+    const bool prof = stats && stats->ev && stats->used + 2 <= stats->nev && stats->used / 2 < 32;
+    if (prof) cudaEventRecord(stats->ev[stats->used], stream);
+    int rc = msm_pair_offsets(s.keys, s.counts, NB, offA, stream); launches++;
+    if (rc) return rc;
+    const Affine<F>* src = d_bases; uint32_t* in = offA; uint32_t* out = offB;
+    uint64_t ubr = s.total;
+    for (int r = 0; r < R; r++) {
+        rc = msm_pair_next_offsets(in, NB, sizes, out, base + o_tmp, scan_tmp, stream); launches += 3;
+        if (rc) return rc;
+        ubr = (ubr + NB + 1) / 2;
+        const unsigned grid = (unsigned)(((ubr + PAIR_K - 1) / PAIR_K + PAIR_THREADS - 1) / PAIR_THREADS);
+        if (r == 0) k_pair_round<F, true><<<grid, PAIR_THREADS, 0, stream>>>(src, s.vals, in, out, NB, P[0], K[0], Ls);
+        else k_pair_round<F, false><<<grid, PAIR_THREADS, 0, stream>>>(src, nullptr, in, out, NB, P[r & 1], K[r & 1], Ls);
+        launches++;
+        src = P[r & 1]; s2.keys = K[r & 1];
+        uint32_t* t = in; in = out; out = t;
+    }
+    rc = msm_pair_counts(in, NB, counts2, stream); launches++;
+    if (rc) return rc;
+    s2.counts = counts2;
+    if (prof) { cudaEventRecord(stats->ev[stats->used + 1], stream); stats->tag[stats->used / 2] = stats->cur_tag; stats->used += 2; }
+    if (stats) stats->launches += launches;
+    // the segmented pipeline on the reduced list; its own accumulate launch is not separately profiled (nev guard)
+    cudaEvent_t* sev = stats ? stats->ev : nullptr; if (stats) stats->ev = nullptr;
+    rc = msm_buckets_impl<F>(src, s2, scratch, o_rest, stream, d_wsum, stats, tail_stream, ev_acc);
+    if (stats) stats->ev = sev;
+    return rc;
+}
+
+template <class F>
+int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratch, size_t scratch_off, cudaStream_t stream,
+                     XYZZ<F>* d_wsum, MsmLaunchStats* stats, cudaStream_t tail_stream, cudaEvent_t ev_acc) {
     const MsmGeom g = s.g;
     const uint32_t NW = g.windows();
     const uint64_t nbuckets = (uint64_t)NW * g.B;
@@ -361,8 +452,9 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     size_t o_hkM = o_hkB + al(heads1 * 4);                     // level-1 keys after the short-run fast path
     size_t o_part = o_hkM + al(heads0 * 4);
     size_t bytes = o_part + al((size_t)NW * ctas_per_window * sizeof(XYZZ<F>));
-    uint8_t* base = (uint8_t*)scratch.get(bytes);
+    uint8_t* base = (uint8_t*)scratch.get(scratch_off + bytes);
     if (!base) return (int)cudaErrorMemoryAllocation;
+    base += scratch_off;
     XYZZ<F>* buckets = (XYZZ<F>*)(base + o_buckets);
     XYZZ<F>* headsA = (XYZZ<F>*)(base + o_headsA); uint32_t* hkA = (uint32_t*)(base + o_hkA);
     XYZZ<F>* headsB = (XYZZ<F>*)(base + o_headsB); uint32_t* hkB = (uint32_t*)(base + o_hkB);

@@ -38,6 +38,7 @@ template <class P> static int check_field(int fid, field_op_t fop, field_const_t
         F d = F::sub(a, b); fop(fid, 1, (uint8_t*)a.v, (uint8_t*)b.v, r); if (memcmp(r, d.v, 4 * N)) { bad++; if (bad < 4) printf("%s sub mismatch it=%d\n", name, it); }
         F n = F::neg(a);    fop(fid, 3, (uint8_t*)a.v, nullptr, r);        if (memcmp(r, n.v, 4 * N)) { bad++; if (bad < 4) printf("%s neg mismatch it=%d\n", name, it); }
         F fm = F::from_mont(a); fop(fid, 6, (uint8_t*)a.v, nullptr, r);    if (memcmp(r, fm.v, 4 * N)) { bad++; if (bad < 4) printf("%s from_mont mismatch it=%d\n", name, it); }
+        if (it < 600) { F ib = F::inv_binary(a); fop(fid, 4, (uint8_t*)a.v, nullptr, r); if (memcmp(r, ib.v, 4 * N)) { bad++; if (bad < 4) printf("%s inv_binary mismatch it=%d\n", name, it); } }
     }
     printf("%s: %s\n", name, bad ? "FAIL" : "ok");
     return bad;
