@@ -650,15 +650,78 @@ int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { if
 int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
 
 // ---------------------------------------------------------------------------------------------------- Groth16
-static int groth16_load_impl(sb_ctx* c, const uint8_t* z, uint64_t zlen, int shard, int n_shards, uint64_t* handle) {
-    if (!c || !z || !handle || n_shards < 1 || shard < 0 || shard >= n_shards) return SB_ERR_ARG;
+// A zkey comes either as a memory image (z != nullptr) or as a file streamed section by section: the small sections
+// (1, 2, 4) are read to the host, the base sections (5-9) go straight to HBM through two pinned staging buffers with
+// cudaMemcpyAsync overlapping the next fread.
+struct ZkeySource {
+    const uint8_t* z = nullptr; uint64_t zlen = 0; FILE* f = nullptr;
+    std::vector<uint8_t> small[5];   // host copies of sections 1, 2, 4 when streaming
+};
+static int zkey_section_table(sb_ctx* c, ZkeySource& src, std::map<uint32_t, Section>& secs) {
+    if (src.z) return parse_binfile(c, src.z, src.zlen, "zkey", 2, secs);
+    uint8_t hd[12];
+    if (fseek(src.f, 0, SEEK_END)) return fail(c, SB_ERR_FORMAT, "zkey: seek failed");
+    const uint64_t flen = (uint64_t)ftell(src.f);
+    fseek(src.f, 0, SEEK_SET);
+    if (fread(hd, 1, 12, src.f) != 12 || memcmp(hd, "zkey", 4) != 0) return fail(c, SB_ERR_FORMAT, "zkey: Invalid File format");
+    uint32_t ver, nsec; memcpy(&ver, hd + 4, 4); memcpy(&nsec, hd + 8, 4);
+    if (ver > 2) return fail(c, SB_ERR_FORMAT, "Version not supported");
+    uint64_t pos = 12;
+    for (uint32_t i = 0; i < nsec; i++) {
+        if (fseek(src.f, (long)pos, SEEK_SET) || fread(hd, 1, 12, src.f) != 12) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        uint32_t id; uint64_t sl; memcpy(&id, hd, 4); memcpy(&sl, hd + 4, 8); pos += 12;
+        if (pos + sl > flen) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        if (secs[id].present) return fail(c, SB_ERR_FORMAT, "Section Duplicated " + std::to_string(id));
+        secs[id].pos = pos; secs[id].len = sl; secs[id].present = true; pos += sl;
+    }
+    if (pos != flen) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+    return 0;
+}
+// host pointer to a small section
+static const uint8_t* zkey_host_section(ZkeySource& src, const std::map<uint32_t, Section>& secs, uint32_t id, int slot) {
+    const Section& s = secs.at(id);
+    if (src.z) return src.z + s.pos;
+    src.small[slot].resize(s.len ? s.len : 1);
+    if (fseek(src.f, (long)s.pos, SEEK_SET) || fread(src.small[slot].data(), 1, s.len, src.f) != s.len) return nullptr;
+    return src.small[slot].data();
+}
+// section bytes [off, off+len) -> device
+static cudaError_t zkey_to_device(sb_ctx* c, ZkeySource& src, const std::map<uint32_t, Section>& secs, uint32_t id, uint64_t off, uint64_t len, void* dst) {
+    if (!len) return cudaSuccess;
+    const Section& s = secs.at(id);
+    if (src.z) return cudaMemcpy(dst, src.z + s.pos + off, len, cudaMemcpyHostToDevice);
+    const size_t CH = 16u << 20;
+    uint8_t* pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2];
+    cudaError_t e = cudaHostAlloc((void**)&pin[0], CH, cudaHostAllocDefault); if (e != cudaSuccess) return e;
+    e = cudaHostAlloc((void**)&pin[1], CH, cudaHostAllocDefault); if (e != cudaSuccess) { cudaFreeHost(pin[0]); return e; }
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    if (fseek(src.f, (long)(s.pos + off), SEEK_SET)) e = cudaErrorUnknown;
+    uint64_t done = 0; int b = 0; bool used[2] = {false, false};
+    while (e == cudaSuccess && done < len) {
+        const size_t n = (size_t)std::min<uint64_t>(CH, len - done);
+        if (used[b]) e = cudaEventSynchronize(ev[b]);                   // staging buffer free again?
+        if (e == cudaSuccess && fread(pin[b], 1, n, src.f) != n) e = cudaErrorUnknown;
+        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)dst + done, pin[b], n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) { cudaEventRecord(ev[b], c->stream); used[b] = true; }
+        done += n; b ^= 1;
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); cudaFreeHost(pin[0]); cudaFreeHost(pin[1]);
+    return e;
+}
+
+static int groth16_load_impl(sb_ctx* c, ZkeySource& src, int shard, int n_shards, uint64_t* handle) {
+    if (!c || (!src.z && !src.f) || !handle || n_shards < 1 || shard < 0 || shard >= n_shards) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     std::map<uint32_t, Section> secs;
-    int rc = parse_binfile(c, z, zlen, "zkey", 2, secs); if (rc) return rc;
+    int rc = zkey_section_table(c, src, secs); if (rc) return rc;
     for (uint32_t id : {1u, 2u, 4u, 5u, 6u, 7u, 8u, 9u}) if (!secs[id].present) return fail(c, SB_ERR_FORMAT, "Missing section " + std::to_string(id));
-    uint32_t proto; memcpy(&proto, z + secs[1].pos, 4);
+    const uint8_t* s1 = zkey_host_section(src, secs, 1, 0);
+    if (!s1 || secs[1].len < 4) return fail(c, SB_ERR_FORMAT, "zkey: short read");
+    uint32_t proto; memcpy(&proto, s1, 4);
     if (proto != 1) return fail(c, SB_ERR_FORMAT, "zkey file is not groth16");
-    const uint8_t* h = z + secs[2].pos; uint64_t hl = secs[2].len;
+    const uint8_t* h = zkey_host_section(src, secs, 2, 1); uint64_t hl = secs[2].len;
+    if (!h) return fail(c, SB_ERR_FORMAT, "zkey: short read");
     const uint32_t n8q = c->n8q, n8r = 32;
     const uint64_t need = 4 + n8q + 4 + n8r + 12 + 3 * 2 * n8q + 3 * 4 * n8q;
     if (hl < need) return fail(c, SB_ERR_FORMAT, "zkey header too short");
@@ -681,10 +744,12 @@ static int groth16_load_impl(sb_ctx* c, const uint8_t* z, uint64_t zlen, int sha
     if (secs[5].len != nv * sG1 || secs[6].len != nv * sG1 || secs[7].len != nv * sG2 ||
         secs[8].len != (nv - k->nPublic - 1) * sG1 || secs[9].len != n * sG1) { delete k; return fail(c, SB_ERR_FORMAT, "zkey section size mismatch"); }
     // coefficient section -> CSR over rows (matrix m, constraint c): src/zkey_utils.js:110-118, groth16_prove.js:147-187
-    uint32_t ncoef; memcpy(&ncoef, z + secs[4].pos, 4);
+    const uint8_t* s4 = zkey_host_section(src, secs, 4, 2);
+    if (!s4 || secs[4].len < 4) { delete k; return fail(c, SB_ERR_FORMAT, "zkey: short read"); }
+    uint32_t ncoef; memcpy(&ncoef, s4, 4);
     const uint64_t sCoef = 12 + n8r;
     if (secs[4].len != 4 + ncoef * sCoef) { delete k; return fail(c, SB_ERR_FORMAT, "zkey coefficient section size mismatch"); }
-    const uint8_t* cf = z + secs[4].pos + 4;
+    const uint8_t* cf = s4 + 4;
     std::vector<uint64_t> rowptr(2 * n + 1, 0);
     for (uint64_t i = 0; i < ncoef; i++) {
         uint32_t m, cc, s; memcpy(&m, cf + i * sCoef, 4); memcpy(&cc, cf + i * sCoef + 4, 4); memcpy(&s, cf + i * sCoef + 8, 4);
@@ -710,18 +775,23 @@ static int groth16_load_impl(sb_ctx* c, const uint8_t* z, uint64_t zlen, int sha
     sb_shard_range(nv, shard, n_shards, &k->wlo, &k->wcnt);
     sb_shard_range(n, shard, n_shards, &k->hlo, &k->hcnt);
     const uint64_t wlo = k->wlo, wcnt = k->wcnt, hlo = k->hlo, hcnt = k->hcnt;
-    up(&k->dA, z + secs[5].pos + wlo * sG1, wcnt * sG1, wcnt * sG1);
-    up(&k->dB1, z + secs[6].pos + wlo * sG1, wcnt * sG1, wcnt * sG1);
-    up(&k->dB2, z + secs[7].pos + wlo * sG2, wcnt * sG2, wcnt * sG2);
+    auto upsec = [&](void** d, uint32_t id, uint64_t off, uint64_t len) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(d, len ? len : 16); if (e != cudaSuccess) return;
+        e = zkey_to_device(c, src, secs, id, off, len, *d);
+    };
+    upsec(&k->dA, 5, wlo * sG1, wcnt * sG1);
+    upsec(&k->dB1, 6, wlo * sG1, wcnt * sG1);
+    upsec(&k->dB2, 7, wlo * sG2, wcnt * sG2);
     // C bases are indexed by signal - (nPublic+1): pad so that one sorted digit list of the witness serves A, B1, B2 and C
     if (e == cudaSuccess) {
         const uint64_t np1 = (uint64_t)k->nPublic + 1;
         e = cudaMalloc(&k->dC, wcnt ? wcnt * sG1 : 16);
         if (e == cudaSuccess && wcnt) e = cudaMemset(k->dC, 0, wcnt * sG1);
         const uint64_t g0 = std::max(wlo, np1), g1 = wlo + wcnt;
-        if (e == cudaSuccess && g1 > g0) e = cudaMemcpy((uint8_t*)k->dC + (g0 - wlo) * sG1, z + secs[8].pos + (g0 - np1) * sG1, (g1 - g0) * sG1, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && g1 > g0) e = zkey_to_device(c, src, secs, 8, (g0 - np1) * sG1, (g1 - g0) * sG1, (uint8_t*)k->dC + (g0 - wlo) * sG1);
     }
-    up(&k->dH, z + secs[9].pos + hlo * sG1, hcnt * sG1, hcnt * sG1);
+    upsec(&k->dH, 9, hlo * sG1, hcnt * sG1);
     up((void**)&k->d_rowptr, rowptr.data(), rowptr.size() * 8, rowptr.size() * 8);
     up((void**)&k->d_sig, sig.data(), (size_t)ncoef * 4, (size_t)ncoef * 4);
     up(&k->d_coef, coef.data(), (size_t)ncoef * 32, (size_t)ncoef * 32);
@@ -742,20 +812,24 @@ static int groth16_load_impl(sb_ctx* c, const uint8_t* z, uint64_t zlen, int sha
     return 0;
 }
 
-int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) { return groth16_load_impl(c, z, zlen, 0, 1, handle); }
+int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) {
+    if (!z) return SB_ERR_ARG;
+    ZkeySource src; src.z = z; src.zlen = zlen; return groth16_load_impl(c, src, 0, 1, handle);
+}
 int sb_groth16_load_sharded(sb_ctx* c, const uint8_t* z, uint64_t zlen, int shard, int n_shards, uint64_t* handle) {
-    return groth16_load_impl(c, z, zlen, shard, n_shards, handle);
+    if (!z) return SB_ERR_ARG;
+    ZkeySource src; src.z = z; src.zlen = zlen; return groth16_load_impl(c, src, shard, n_shards, handle);
 }
 
 int sb_groth16_load_file(sb_ctx* c, const char* path, uint64_t* handle) {
     if (!c || !path) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
     FILE* f = fopen(path, "rb");
     if (!f) return fail(c, SB_ERR_FORMAT, std::string("cannot open ") + path);
-    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> buf((size_t)sz);
-    size_t rd = fread(buf.data(), 1, (size_t)sz, f); fclose(f);
-    if (rd != (size_t)sz) return fail(c, SB_ERR_FORMAT, "short read");
-    return sb_groth16_load(c, buf.data(), buf.size(), handle);
+    ZkeySource src; src.f = f;
+    int rc = groth16_load_impl(c, src, 0, 1, handle);
+    fclose(f);
+    return rc;
 }
 
 static Groth16Key* get_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->keys.size()) ? c->keys[h - 1] : nullptr; }

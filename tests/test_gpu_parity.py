@@ -407,3 +407,41 @@ def test_msm_pairing_rounds_experimental(bn):
             assert bn.G2.toAffine(bn.G2.multiExpRegistered(h, sc.reshape(-1))).tobytes() == want2
     finally:
         bn.lib.sb_set_tuning(4, 0); bn.lib.sb_set_tuning(5, 0)
+
+
+def test_plonk_polynomial_wrappers_on_fixture_goldens(bn, golden):
+    """the PLONK/fflonk call sites (Polynomial.fromEvaluations / to4T / multiExponentiation,
+    Evaluations.fromPolynomial) reproduce the reference-written bytes of the committed PLONK zkeys."""
+    from snarkjs_b200.polynomial import Polynomial, Evaluations
+    gn, gm = golden("ntt_goldens.npz"), golden("msm_g1_goldens.npz")
+    for tag, lab, name in (("plonk2048", "QM", "Qm"), ("plonk8", "QM", "Qm"), ("plonk8", "S1", "S1")):
+        coef, evals = gn[f"{tag}_{lab}_coef"], gn[f"{tag}_{lab}_evals"]
+        p = Polynomial(coef, bn)
+        assert np.array_equal(Evaluations.fromPolynomial(p, 4, bn).eval, evals)                      # evaluations.js:29-36
+        assert np.array_equal(Polynomial.fromEvaluations(evals, bn).coef[:coef.size], coef)          # polynomial.js:31-35
+        assert p.multiExponentiation(gm[f"{tag}_ptau"], name).tobytes() == gm[f"{tag}_{name}_commit"].tobytes()   # :970-977
+        n = coef.size // 32
+        a, A4 = Polynomial.to4T(O.fr_fft(BN, coef), n, bn.Fr)                                         # :111-119
+        assert np.array_equal(a, coef) and np.array_equal(A4, evals)
+
+
+def test_groth16_streamed_zkey_file(bn, golden, tmp_path):
+    """sb_groth16_load_file: sections streamed from disk through pinned double buffers; same proof as the in-memory
+    load; malformed files are rejected with the reference's messages."""
+    from snarkjs_b200 import groth16, SbError
+    g = golden("groth16_case.npz")
+    zkey, wt = g["zkey"].tobytes(), g["wtns"].tobytes()
+    p = tmp_path / "circuit.zkey"
+    p.write_bytes(zkey)
+    ci = O.CURVES[BN]
+    r, s = ci.fr_to_mont(77), ci.fr_to_mont(88)
+    pk_mem = groth16.ProvingKey(zkey, curve=bn)
+    pk_file = groth16.ProvingKey.from_file(str(p), bn)
+    assert (pk_file.nVars, pk_file.nPublic, pk_file.domainSize) == (pk_mem.nVars, pk_mem.nPublic, pk_mem.domainSize)
+    assert groth16.prove(pk_file, wt, r, s) == groth16.prove(pk_mem, wt, r, s)
+    (tmp_path / "short.zkey").write_bytes(zkey[:len(zkey) - 100])
+    with pytest.raises(SbError, match="Invalid file size"):
+        groth16.ProvingKey.from_file(str(tmp_path / "short.zkey"), bn)
+    with pytest.raises(SbError, match="cannot open"):
+        groth16.ProvingKey.from_file(str(tmp_path / "missing.zkey"), bn)
+    pk_mem.release(); pk_file.release()
