@@ -116,8 +116,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    log_n = args.cpu_log_n or 16
-    steps = max(1, min(args.steps, 3))
+    log_n = args.cpu_log_n or min(18, args.log_n)
+    steps = max(1, min(args.steps, 2))
     dt, cores = cpu_reference_run(log_n, steps, args.warmup)
     scale = (1 << args.log_n) / (1 << log_n)
     val = 1.0 / (dt * scale)
@@ -277,7 +277,7 @@ def run_b200(args):
     }
     if not args.no_cpu_baseline:
         try:
-            log_s = args.cpu_log_n or 15
+            log_s = args.cpu_log_n or min(16, L)
             dt, cores = cpu_reference_run(log_s, 1, 0)
             scale = (1 << L) / (1 << log_s)
             line["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": "proofs/s", "cores": cores, "kind": "port",
