@@ -298,7 +298,7 @@ float elapsed(sb_ctx* c, int a, int b) { float ms = 0; cudaEventElapsedTime(&ms,
 // ------------------------------------------------------------------------------------------------------------
 int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const uint8_t* d_scalars, uint32_t sbytes, uint64_t n,
                        uint8_t* acc_xyzz, const MsmGeom* gp = nullptr, uint64_t first = 0) {
-    static const uint64_t MAXC = 1ull << 23;
+    const uint64_t MAXC = 1ull << (g_msm_tuning[6] > 0 ? g_msm_tuning[6] : 23);   // points per MSM chunk (tuning key 6: test hook)
     for (uint64_t off = 0; off < n; off += MAXC) {
         uint64_t cn = std::min(MAXC, n - off);
         MsmGeom g = msm_geometry(cn, sbytes, c->fr_bits);
@@ -885,7 +885,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
     uint8_t* pA = partials; uint8_t* pB1 = pA + G1.xyzz_bytes; uint8_t* pC = pB1 + G1.xyzz_bytes; uint8_t* pH = pC + G1.xyzz_bytes; uint8_t* pB2 = pH + G1.xyzz_bytes;
     memset(partials, 0, 4 * G1.xyzz_bytes + G2.xyzz_bytes);
-    static const uint64_t MAXC = 1ull << 23;
+    const uint64_t MAXC = 1ull << (g_msm_tuning[6] > 0 ? g_msm_tuning[6] : 23);   // points per MSM chunk (tuning key 6: test hook)
     uint64_t wlo, wcnt; range(nv, wlo, wcnt);
     uint64_t hlo, hcnt; range(n, hlo, hcnt);
     // a key loaded with sb_groth16_load_sharded only holds its own ranges: local indexing

@@ -14,6 +14,7 @@ namespace sb {
 // Fp2 = Fp[u]/(u^2+1)  (reference build_f2m 4028; mul 4157; square 4216).  Byte order c0 || c1.
 template <class P> struct Fp2 {
     typedef Fp<P> B;
+    static constexpr bool HAS_MUL2 = false;
     B a, b;
     SB_HD static Fp2 one() { Fp2 r; r.a = B::one(); r.b = B::zero(); return r; }
     SB_HD static Fp2 inv(const Fp2& x) {   // (a - bu)/(a^2 + b^2)
@@ -92,7 +93,9 @@ template <class F> struct XYZZ {
         }
         F PP = F::sqr_i(Pp), PPP = F::mul_i(Pp, PP), Q = F::mul_i(x, PP);
         F X3 = F::sub(F::sub(F::sqr_i(R), PPP), F::dbl(Q));
-        F Y3 = F::sub(F::mul_i(R, F::sub(Q, X3)), F::mul_i(y, PPP));
+        F Y3;
+        if constexpr (F::HAS_MUL2) Y3 = F::mul2_i(R, F::sub(Q, X3), F::neg(y), PPP);   // R(Q - X3) - Y1*PPP, one reduction
+        else Y3 = F::sub(F::mul_i(R, F::sub(Q, X3)), F::mul_i(y, PPP));
         x = X3; y = Y3; zz = F::mul_i(zz, PP); zzz = F::mul_i(zzz, PPP);
     }
     // acc += q   (add-2008-s)

@@ -108,6 +108,7 @@ inline void subc(uint32_t& r, uint32_t a, uint32_t b)    { r = emu_sub(a, b, g_c
 // ---------------------------------------------------------------------------------------------
 template <class P> struct Fp {
     static constexpr int N = P::N;
+    static constexpr bool HAS_MUL2 = P::p(P::N - 1) < 0x55555555u;   // 3p < R: the dual-product multiply applies
     uint32_t v[N];
 
     SB_HD static Fp zero() { Fp r;
@@ -252,6 +253,79 @@ _Pragma("unroll")
 #endif
     }
     SB_HD static Fp sqr(const Fp& a) { return mul(a, a); }
+
+    // Dual-product Montgomery multiply: (x*y + u*v) * R^-1 mod p with ONE interleaved reduction — 3N^2 wide MACs instead
+    // of the 4N^2 of two multiplies.  Requires 3p < R so that the running sum (< 3p) fits N limbs; result < p(1 + 2p/R).
+    SB_HD static void row2(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi, const uint32_t* u, uint32_t vi) {
+        ptx::add_cc(Y[0], Y[0], X[1]);
+_Pragma("unroll")
+        for (int j = 0; j < N - 2; j += 2) {
+            ptx::madc_lo_cc3(X[j], a[j + 1], bi, X[j + 2]);
+            ptx::madc_hi_cc3(X[j + 1], a[j + 1], bi, X[j + 3]);
+        }
+        ptx::madc_lo_cc3(X[N - 2], a[N - 1], bi, 0);
+        ptx::madc_hi3(X[N - 1], a[N - 1], bi, 0);
+        ptx::mad_lo_cc(Y[0], a[0], bi);
+        ptx::madc_hi_cc(Y[1], a[0], bi);
+_Pragma("unroll")
+        for (int j = 2; j < N; j += 2) {
+            ptx::madc_lo_cc(Y[j], a[j], bi);
+            ptx::madc_hi_cc(Y[j + 1], a[j], bi);
+        }
+        ptx::addc(X[N - 1], X[N - 1], 0);
+        add_product(X, Y, u, vi);
+        reduce(X, Y);
+    }
+    // X (columns 1..N) += u_odd * vi ; Y (columns 0..N-1) += u_even * vi, carry of Y into X[N-1]
+    SB_HD static void add_product(uint32_t* X, uint32_t* Y, const uint32_t* u, uint32_t vi) {
+        ptx::mad_lo_cc(X[0], u[1], vi);
+        ptx::madc_hi_cc(X[1], u[1], vi);
+_Pragma("unroll")
+        for (int j = 2; j < N; j += 2) {
+            ptx::madc_lo_cc(X[j], u[j + 1], vi);
+            ptx::madc_hi_cc(X[j + 1], u[j + 1], vi);
+        }
+        ptx::mad_lo_cc(Y[0], u[0], vi);
+        ptx::madc_hi_cc(Y[1], u[0], vi);
+_Pragma("unroll")
+        for (int j = 2; j < N; j += 2) {
+            ptx::madc_lo_cc(Y[j], u[j], vi);
+            ptx::madc_hi_cc(Y[j + 1], u[j], vi);
+        }
+        ptx::addc(X[N - 1], X[N - 1], 0);
+    }
+    SB_HD static Fp mul2(const Fp& x, const Fp& y, const Fp& u, const Fp& v) {
+        static_assert(P::p(N - 1) < 0x55555555u, "mul2 needs 3p < R");
+#if !defined(__CUDA_ARCH__) && !defined(SB_HOST_EMULATE_PTX)
+        return add(host_mul(x, y), host_mul(u, v));
+#else
+        uint32_t E[N], O[N];
+_Pragma("unroll")
+        for (int j = 0; j < N; j += 2) {
+            E[j] = ptx::mul_lo(x.v[j], y.v[0]);     E[j + 1] = ptx::mul_hi(x.v[j], y.v[0]);
+            O[j] = ptx::mul_lo(x.v[j + 1], y.v[0]); O[j + 1] = ptx::mul_hi(x.v[j + 1], y.v[0]);
+        }
+        add_product(O, E, u.v, v.v[0]);
+        reduce(O, E);
+_Pragma("unroll")
+        for (int i = 1; i < N; i += 2) {
+            row2(E, O, x.v, y.v[i], u.v, v.v[i]);
+            if (i + 1 < N) row2(O, E, x.v, y.v[i + 1], u.v, v.v[i + 1]);
+        }
+        Fp r;
+        ptx::add_cc(r.v[0], E[0], O[1]);
+_Pragma("unroll")
+        for (int i = 1; i < N - 1; i++) ptx::addc_cc(r.v[i], E[i], O[i + 1]);
+        ptx::addc(r.v[N - 1], E[N - 1], 0);
+        final_sub(r.v);
+        return r;
+#endif
+    }
+    // x*y + u*v for the hot loop: dual product where the modulus allows it, two multiplies otherwise
+    SB_HD static Fp mul2_i(const Fp& x, const Fp& y, const Fp& u, const Fp& v) {
+        if constexpr (P::p(N - 1) < 0x55555555u) return mul2(x, y, u, v);
+        else return add(mul(x, y), mul(u, v));
+    }
     SB_HD static Fp mul_i(const Fp& a, const Fp& b) { return mul(a, b); }
     SB_HD static Fp sqr_i(const Fp& a) { return mul(a, a); }
     SB_HD static Fp to_mont(const Fp& a) { return mul(a, r2()); }

@@ -146,6 +146,10 @@ class ProvingKey:
     def from_file(cls, path: str, curve: Curve):
         """Streams the .zkey from disk (sb_groth16_load_file): base sections go to HBM through pinned double buffers."""
         self = cls.__new__(cls)
+        self.curve, self._own_curve = curve, False
+        h = ctypes.c_uint64()
+        curve.check(curve.lib.sb_groth16_load_file(curve.handle, path.encode(), ctypes.byref(h)))   # validates the container
+        self.handle = h.value
         with open(path, "rb") as f:
             head = f.read(1 << 16)
         # header only (sections 1-2 are at the front in files written by snarkjs; fall back to a full read otherwise)
@@ -153,10 +157,6 @@ class ProvingKey:
             self.header = read_zkey_header_groth16_prefix(head)
         except Exception:
             self.header = read_zkey_header_groth16(open(path, "rb").read())
-        self.curve, self._own_curve = curve, False
-        h = ctypes.c_uint64()
-        curve.check(curve.lib.sb_groth16_load_file(curve.handle, path.encode(), ctypes.byref(h)))
-        self.handle = h.value
         nv, npub, ds = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         curve.check(curve.lib.sb_groth16_info(curve.handle, self.handle, ctypes.byref(nv), ctypes.byref(npub), ctypes.byref(ds)))
         self.nVars, self.nPublic, self.domainSize = nv.value, npub.value, ds.value

@@ -38,6 +38,18 @@ template <class P> static int check_field(int fid, field_op_t fop, field_const_t
         F d = F::sub(a, b); fop(fid, 1, (uint8_t*)a.v, (uint8_t*)b.v, r); if (memcmp(r, d.v, 4 * N)) { bad++; if (bad < 4) printf("%s sub mismatch it=%d\n", name, it); }
         F n = F::neg(a);    fop(fid, 3, (uint8_t*)a.v, nullptr, r);        if (memcmp(r, n.v, 4 * N)) { bad++; if (bad < 4) printf("%s neg mismatch it=%d\n", name, it); }
         F fm = F::from_mont(a); fop(fid, 6, (uint8_t*)a.v, nullptr, r);    if (memcmp(r, fm.v, 4 * N)) { bad++; if (bad < 4) printf("%s from_mont mismatch it=%d\n", name, it); }
+        if constexpr (P::p(N - 1) < 0x55555555u) {   // dual-product multiply vs two oracle multiplies + add
+            F c2, d2; for (int i = 0; i < N; i++) { c2.v[i] = (uint32_t)rnd(); d2.v[i] = (uint32_t)rnd(); }
+            c2.v[N - 1] &= mask; d2.v[N - 1] &= mask;
+            if (it == 3) { for (int i = 0; i < N; i++) { c2.v[i] = p[i]; d2.v[i] = p[i]; } c2.v[0] -= 1; d2.v[0] -= 1; a = c2; b = d2; }
+            // canonicalise the random operands through the oracle (add 0)
+            uint8_t z0[48] = {0}; uint8_t t1[48], t2[48], t3[48];
+            fop(fid, 0, (uint8_t*)c2.v, z0, t1); memcpy(c2.v, t1, 4 * N); fop(fid, 0, (uint8_t*)d2.v, z0, t1); memcpy(d2.v, t1, 4 * N);
+            F aa, bb; fop(fid, 0, (uint8_t*)a.v, z0, t1); memcpy(aa.v, t1, 4 * N); fop(fid, 0, (uint8_t*)b.v, z0, t1); memcpy(bb.v, t1, 4 * N);
+            F m2 = F::mul2(aa, bb, c2, d2);
+            fop(fid, 2, (uint8_t*)aa.v, (uint8_t*)bb.v, t1); fop(fid, 2, (uint8_t*)c2.v, (uint8_t*)d2.v, t2); fop(fid, 0, t1, t2, t3);
+            if (memcmp(t3, m2.v, 4 * N)) { bad++; if (bad < 4) printf("%s mul2 mismatch it=%d\n", name, it); }
+        }
         if (it < 600) { F ib = F::inv_binary(a); fop(fid, 4, (uint8_t*)a.v, nullptr, r); if (memcmp(r, ib.v, 4 * N)) { bad++; if (bad < 4) printf("%s inv_binary mismatch it=%d\n", name, it); } }
     }
     printf("%s: %s\n", name, bad ? "FAIL" : "ok");

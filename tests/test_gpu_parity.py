@@ -445,3 +445,30 @@ def test_groth16_streamed_zkey_file(bn, golden, tmp_path):
     with pytest.raises(SbError, match="cannot open"):
         groth16.ProvingKey.from_file(str(tmp_path / "missing.zkey"), bn)
     pk_mem.release(); pk_file.release()
+
+
+def test_chunked_paths(bn, golden):
+    """Inputs larger than one MSM chunk (2^23 points in production) take the chunk loop of sb_msm_* and the serial
+    fallback of the Groth16 pipeline; sb_set_tuning(6, 11) shrinks the chunk to 2^11 so the tests reach them."""
+    from snarkjs_b200 import groth16
+    n = 9000
+    bases = O.gen_points(BN, 1, 51, n)
+    sc = rand_fr(52, n)
+    want = O.g_to_affine(BN, 1, O.multiexp_affine(BN, 1, bases, sc))
+    g = golden("groth16_case.npz")
+    zkey, wt = g["zkey"].tobytes(), g["wtns"].tobytes()
+    ci = O.CURVES[BN]
+    r, s = ci.fr_to_mont(5150), ci.fr_to_mont(1984)
+    oproof, _ = O.groth16_prove(zkey, wt, r, s)
+    bn.lib.sb_set_tuning(6, 11)
+    try:
+        assert bn.G1.toAffine(bn.G1.multiExpAffine(bases, sc)).tobytes() == want
+        h = bn.G1.registerBases(bases)
+        assert bn.G1.toAffine(bn.G1.multiExpRegistered(h, sc)).tobytes() == want
+        pk = groth16.ProvingKey(zkey, curve=bn)          # domain 1024 < chunk, nVars 1003 < chunk: shrink further
+        bn.lib.sb_set_tuning(6, 8)
+        proof, _ = groth16.prove(pk, wt, r, s)
+        assert proof == oproof
+        pk.release()
+    finally:
+        bn.lib.sb_set_tuning(6, 0)
