@@ -16,7 +16,7 @@
 #include "fr_entry.h"
 
 using namespace sb;
-namespace sb { double calibrate(int what, cudaStream_t stream); }
+namespace sb { double calibrate(int what, cudaStream_t stream); extern int g_ntt_tile_log; }
 
 namespace {
 
@@ -623,7 +623,10 @@ int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) {
     return c->fr_s;
 }
 
-int sb_set_tuning(int key, int value) { if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0; }
+int sb_set_tuning(int key, int value) {
+    if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
+    if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
+}
 double sb_last_stat(sb_ctx* c, int which) { return (c && which >= 0 && which < 8) ? c->stat[which] : 0.0; }
 double sb_calibrate(sb_ctx* c, int what) { if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
 int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out) {

@@ -176,6 +176,7 @@ __global__ void k_qap_rows(const uint64_t* __restrict__ row_ptr, const uint32_t*
 // ------------------------------------------------------------------------------------------------
 struct NttPlan { int npass; int deg[8]; int logc[8]; };
 
+extern int g_ntt_tile_log;   // log2 of the largest tile (elements); 12 = 128 KiB smem (1 CTA/SM), 11 = 64 KiB (3 CTAs/SM)
 inline NttPlan ntt_plan(int L) {
     NttPlan pl{};
     if (L <= NTT_DMAX) { pl.npass = 1; pl.deg[0] = L; pl.logc[0] = 0; if (L == 0) pl.npass = 0; return pl; }
@@ -184,7 +185,7 @@ inline NttPlan ntt_plan(int L) {
     pl.npass = np;
     for (int i = 0; i < np; i++) {
         pl.deg[i] = base + (i < rem ? 1 : 0);
-        int lc = 12 - pl.deg[i]; if (lc > 3) lc = 3;
+        int lc = g_ntt_tile_log - pl.deg[i]; if (lc > 3) lc = 3; if (lc < 0) lc = 0;
         if (lc > L - pl.deg[i]) lc = L - pl.deg[i];
         pl.logc[i] = lc;
     }
