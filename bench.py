@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 domain of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check-oracle", action="store_true", help="also prove the full workload with the CPU oracle and compare proof bytes (minutes)")
     return ap.parse_args()
 
 
@@ -274,6 +275,7 @@ def run_b200(args):
                          "peak": peak_modmul / 1e9, "frac": ach_mod / peak_modmul if peak_modmul > 0 else None,
                          "peak_source": "sb_calibrate(1): four independent per-thread BN254 Fq Montgomery-multiply chains (IMAD.WIDE.U32.X issue-bound), measured on this GPU in this run", "all_accumulate_kernels_frac": (all_mod / (all_ms * 1e-3)) / peak_modmul if (all_ms > 0 and peak_modmul > 0) else None},
         "breakdown_ms": brk, "accumulate": acc, "setup_s": t_setup,
+        "proof_sha256": __import__("hashlib").sha256(proof.tobytes()).hexdigest(),   # same inputs => same bytes at every N
     }
     if not args.no_cpu_baseline:
         try:
@@ -284,6 +286,12 @@ def run_b200(args):
                                     "sample": f"oracle (restated reference prover) on the chain circuit at domain 2^{log_s}: {dt:.3f} s, scaled x{scale:g} linearly to 2^{L}"}
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"error": str(e)}
+    if args.check_oracle:
+        from oracle import oracle as O
+        ci = O.CURVES[O.BN254]
+        t0 = time.perf_counter()
+        oproof, _ = O.groth16_prove(zkey, synth.wtns_container(curve.r, wit_np), r, s, concurrency=O.lib().or_num_threads())
+        line["oracle_check"] = {"match": groth16.proof_to_object(curve, proof.tobytes()) == oproof, "oracle_seconds": time.perf_counter() - t0}
     print(json.dumps(line))
     pk.release()
     curve.terminate()
