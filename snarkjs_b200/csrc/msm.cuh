@@ -246,6 +246,75 @@ k_reduce(const XYZZ<F>* __restrict__ buckets, MsmGeom g, XYZZ<F>* __restrict__ p
     if (threadIdx.x == 0) store_vec(partials + (uint64_t)w * ctas_per_window + cta, load_vec(sm));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Hierarchical bucket reduction (used when a window has >= 2048 buckets).  For a block of buckets [b0, b0+n):
+//   R = sum B_b,   S = sum (b - b0 + 1) * B_b.
+// m adjacent blocks of n buckets combine as  R = sum R_i,  S = sum S_i + n * sum_i i*R_i, where sum_i i*R_i is again a
+// running sum (t += R_i; acc += t from the top).  So every level costs ~3 additions per child and log2(n) doublings
+// per parent — no per-thread scalar multiply as in k_reduce (which spends ~40 % of its work there).
+// k_reduce2: one CTA = 128 threads x 16 buckets (level 1) -> 16 groups of 8 -> 4 groups of 4 -> 1: (R, S) of 2048 buckets.
+// k_window_sum2: one CTA per window folds the per-CTA (R, S) pairs, 8 at a time, down to the window total S.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void combine_children(const XYZZ<F>* Rin, const XYZZ<F>* Sin, int m, int log_n, XYZZ<F>& Rout, XYZZ<F>& Sout) {
+    XYZZ<F> t = XYZZ<F>::inf(), acc = XYZZ<F>::inf(), ssum = load_vec(Sin);
+    for (int i = m - 1; i >= 1; i--) {
+        XYZZ<F> r = load_vec(Rin + i), s = load_vec(Sin + i);
+        t.add(r); acc.add(t); ssum.add(s);
+    }
+    for (int k = 0; k < log_n; k++) acc = XYZZ<F>::dbl(acc);
+    ssum.add(acc);
+    XYZZ<F> r0 = load_vec(Rin); t.add(r0);
+    Rout = t; Sout = ssum;
+}
+
+static constexpr int RED2_L = 16, RED2_THREADS = 128, RED2_BUCKETS = RED2_L * RED2_THREADS;   // 2048 buckets per CTA
+
+template <class F>
+__global__ void __launch_bounds__(RED2_THREADS)
+k_reduce2(const XYZZ<F>* __restrict__ buckets, MsmGeom g, XYZZ<F>* __restrict__ outR, XYZZ<F>* __restrict__ outS) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    XYZZ<F>* R1 = sm; XYZZ<F>* S1 = sm + 128; XYZZ<F>* R2 = sm + 256; XYZZ<F>* S2 = sm + 272; XYZZ<F>* R3 = sm + 288; XYZZ<F>* S3 = sm + 292;
+    const uint32_t tid = threadIdx.x;
+    const XYZZ<F>* bk = buckets + (uint64_t)blockIdx.x * RED2_BUCKETS + (uint64_t)tid * RED2_L;
+    {   // level 1: classic running sum over 16 buckets
+        XYZZ<F> run = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
+        for (int b = RED2_L - 1; b >= 0; b--) { XYZZ<F> p = load_vec(bk + b); run.add(p); sum.add(run); }
+        store_vec(R1 + tid, run); store_vec(S1 + tid, sum);
+    }
+    __syncthreads();
+    if (tid < 16) { XYZZ<F> r, s; combine_children<F>(R1 + 8 * tid, S1 + 8 * tid, 8, 4, r, s); store_vec(R2 + tid, r); store_vec(S2 + tid, s); }   // n = 16
+    __syncthreads();
+    if (tid < 4) { XYZZ<F> r, s; combine_children<F>(R2 + 4 * tid, S2 + 4 * tid, 4, 7, r, s); store_vec(R3 + tid, r); store_vec(S3 + tid, s); }      // n = 128
+    __syncthreads();
+    if (tid == 0) { XYZZ<F> r, s; combine_children<F>(R3, S3, 4, 9, r, s); store_vec(outR + blockIdx.x, r); store_vec(outS + blockIdx.x, s); }      // n = 512
+}
+
+// per window: NC = B / 2048 pairs (power of two, <= 1024) -> S of the window.  One CTA of 128 threads per window.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_window_sum2(const XYZZ<F>* __restrict__ inR, const XYZZ<F>* __restrict__ inS, uint32_t NC, XYZZ<F>* __restrict__ out) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);     // two ping-pong regions of (R[128], S[128])
+    const uint32_t tid = threadIdx.x;
+    const XYZZ<F>* Rin = inR + (uint64_t)blockIdx.x * NC; const XYZZ<F>* Sin = inS + (uint64_t)blockIdx.x * NC;
+    uint32_t n = NC; int log_block = 11;                    // a child covers 2^11 buckets at the first level
+    int ping = 0;
+    while (n > 1) {
+        const uint32_t m = n >= 8 ? 8 : n, parents = n / m;
+        XYZZ<F>* Rout = sm + ping * 256; XYZZ<F>* Sout = Rout + 128;
+        for (uint32_t p = tid; p < parents; p += blockDim.x) {
+            XYZZ<F> r, s; combine_children<F>(Rin + (uint64_t)p * m, Sin + (uint64_t)p * m, (int)m, log_block, r, s);
+            store_vec(Rout + p, r); store_vec(Sout + p, s);
+        }
+        __syncthreads();
+        Rin = Rout; Sin = Sout; n = parents; ping ^= 1;
+        log_block += (m == 8 ? 3 : m == 4 ? 2 : 1);
+    }
+    if (tid == 0) store_vec(out + blockIdx.x, load_vec(Sin));
+}
+
 // one warp per window: lanes stride over the per-CTA partials of k_reduce, then a shared-memory tree
 template <class F>
 __global__ void __launch_bounds__(32)
@@ -393,7 +462,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
         const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
         const uint32_t ctas_per_window = (g.B / L + 127) / 128;
         size_t need = al(NBl * sizeof(XYZZ<F>)) + al(heads0 * sizeof(XYZZ<F>)) + al(heads0 * 4) + al(heads1 * sizeof(XYZZ<F>)) + al(heads1 * 4) +
-                      al(heads0 * 4) + al((size_t)g.windows() * ctas_per_window * sizeof(XYZZ<F>));
+                      al(heads0 * 4) + al((size_t)2 * g.windows() * ctas_per_window * sizeof(XYZZ<F>));
         need += need / 8 + (1u << 20);   // margin: the impl must never grow (= reallocate) the scratch the rounds are using
         if (!scratch.get(o_rest + need)) return (int)cudaErrorMemoryAllocation;
     }
@@ -451,7 +520,7 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
     size_t o_headsB = o_hkA + al(heads0 * 4), o_hkB = o_headsB + al(heads1 * sizeof(XYZZ<F>));
     size_t o_hkM = o_hkB + al(heads1 * 4);                     // level-1 keys after the short-run fast path
     size_t o_part = o_hkM + al(heads0 * 4);
-    size_t bytes = o_part + al((size_t)NW * ctas_per_window * sizeof(XYZZ<F>));
+    size_t bytes = o_part + al((size_t)2 * NW * ctas_per_window * sizeof(XYZZ<F>));   // x2: (R, S) pairs of k_reduce2
     uint8_t* base = (uint8_t*)scratch.get(scratch_off + bytes);
     if (!base) return (int)cudaErrorMemoryAllocation;
     base += scratch_off;
@@ -501,8 +570,23 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
         }
     }
     if (!heads0 && tail_stream && tail_stream != stream && ev_acc) { cudaEventRecord(ev_acc, stream); cudaStreamWaitEvent(tail_stream, ev_acc, 0); stream = tail_stream; }
-    k_reduce<F><<<NW * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
-    k_window_sum<F><<<NW, 32, 32 * sizeof(XYZZ<F>), stream>>>(partials, ctas_per_window, d_wsum); launches++;
+    if (g.B >= (uint32_t)RED2_BUCKETS && g.B / RED2_BUCKETS <= 1024 && g_msm_tuning[1] == 2) {   // experimental: less work (-36 %) but 2-3x the
+        // dependent-add latency of k_reduce; measured slower (proof 27.4 ms vs 26.0 ms overlapped, 31.3 vs 26.6 serialised)
+        // hierarchical reduction: per-CTA (R, S) pairs live in the partials area (2 * NC entries per window <= ctas_per_window)
+        const uint32_t NC = g.B / RED2_BUCKETS;
+        XYZZ<F>* pR = partials; XYZZ<F>* pS = partials + (size_t)NW * NC;
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(296 * sizeof(XYZZ<F>)));
+            cudaFuncSetAttribute(k_window_sum2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * sizeof(XYZZ<F>)));
+            configured = true;
+        }
+        k_reduce2<F><<<NW * NC, RED2_THREADS, 296 * sizeof(XYZZ<F>), stream>>>(buckets, g, pR, pS); launches++;
+        k_window_sum2<F><<<NW, 128, 512 * sizeof(XYZZ<F>), stream>>>(pR, pS, NC, d_wsum); launches++;
+    } else {
+        k_reduce<F><<<NW * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
+        k_window_sum<F><<<NW, 32, 32 * sizeof(XYZZ<F>), stream>>>(partials, ctas_per_window, d_wsum); launches++;
+    }
     if (stats) stats->launches += launches;
     return (int)cudaGetLastError();
 }
