@@ -116,6 +116,26 @@ template <class P> static int check_g1(int curve, int fid, field_op_t fop, field
     return bad;
 }
 
+// Fp2 multiply (dual-product schoolbook) against Karatsuba built from single multiplies, and squaring against mul
+template <class P> static int check_fp2(const char* name) {
+    typedef Fp<P> B; typedef Fp2<P> F2; const int N = P::N;
+    int bad = 0;
+    for (int it = 0; it < 5000; it++) {
+        F2 x, y; B* parts[4] = {&x.a, &x.b, &y.a, &y.b};
+        for (B* q : parts) { for (int i = 0; i < N; i++) q->v[i] = (uint32_t)rnd(); q->v[N - 1] &= 0x0fffffffu; *q = B::add(*q, B::zero()); }
+        if (it == 0) { x.a = B::zero(); }
+        if (it == 1) { for (B* q : parts) { for (int i = 0; i < N; i++) q->v[i] = P::p(i); q->v[0] -= 1; } }
+        F2 m = F2::mul_i(x, y);
+        B A = B::mul(x.a, y.a), Bb = B::mul(x.b, y.b), C = B::mul(B::add(x.a, x.b), B::add(y.a, y.b));
+        B c0 = B::sub(A, Bb), c1 = B::sub(B::sub(C, A), Bb);
+        if (!(m.a == c0) || !(m.b == c1)) { bad++; if (bad < 4) printf("%s fp2 mul mismatch it=%d\n", name, it); }
+        F2 s = F2::sqr_i(x), s2 = F2::mul_i(x, x);
+        if (!(s == s2)) { bad++; if (bad < 4) printf("%s fp2 sqr mismatch it=%d\n", name, it); }
+    }
+    printf("%s: %s\n", name, bad ? "FAIL" : "ok");
+    return bad;
+}
+
 int main(int argc, char** argv) {
     void* h = dlopen(argc > 1 ? argv[1] : "oracle/liboracle.so", RTLD_NOW);
     if (!h) { printf("dlopen failed: %s\n", dlerror()); return 2; }
@@ -132,6 +152,8 @@ int main(int argc, char** argv) {
     // generators in Montgomery affine form are passed on argv as hex? simpler: derive from oracle toMont of (1,2)
     { uint8_t g[64] = {0}, gm[64]; g[0] = 1; g[32] = 2; fop(0, 5, g, nullptr, gm); fop(0, 5, g + 32, nullptr, gm + 32);
       bad += check_g1<BnFq>(0, 0, fop, fconst, gop, gen, gm, "BN254 G1 XYZZ"); }
+    bad += check_fp2<BnFq>("BN254 Fq2");
+    bad += check_fp2<BlsFq>("BLS12-381 Fq2");
     printf(bad ? "HOST CHECK FAILED\n" : "HOST CHECK PASSED\n");
     return bad ? 1 : 0;
 }
