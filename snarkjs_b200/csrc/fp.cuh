@@ -321,6 +321,94 @@ _Pragma("unroll")
         return r;
 #endif
     }
+    // ---- double-width product and stand-alone Montgomery reduction (for lazily reduced Fq2 arithmetic) -------------
+    // T[0..2N) = a * b.  Two column-aligned accumulator arrays E (even columns) / O (O[k] = column k+1) as in mul();
+    // every chain's carry-out lands in a limb that so far only holds earlier carry bits.  N^2 wide MACs.
+    SB_HD static void mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* T) {
+        uint32_t E[2 * N], O[2 * N];
+_Pragma("unroll")
+        for (int k = 0; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
+_Pragma("unroll")
+        for (int i = 0; i < N; i++) {
+            const uint32_t bi = b[i];
+            if ((i & 1) == 0) {
+                // even row: even j -> E[i+j], odd j -> O[i+j-1]
+                ptx::mad_lo_cc(E[i], a[0], bi); ptx::madc_hi_cc(E[i + 1], a[0], bi);
+_Pragma("unroll")
+                for (int j = 2; j < N; j += 2) { ptx::madc_lo_cc(E[i + j], a[j], bi); ptx::madc_hi_cc(E[i + j + 1], a[j], bi); }
+                ptx::addc(E[i + N], E[i + N], 0);
+                ptx::mad_lo_cc(O[i], a[1], bi); ptx::madc_hi_cc(O[i + 1], a[1], bi);
+_Pragma("unroll")
+                for (int j = 3; j < N; j += 2) { ptx::madc_lo_cc(O[i + j - 1], a[j], bi); ptx::madc_hi_cc(O[i + j], a[j], bi); }
+                ptx::addc(O[i + N], O[i + N], 0);
+            } else {
+                // odd row: odd j -> E[i+j], even j -> O[i+j-1]
+                ptx::mad_lo_cc(E[i + 1], a[1], bi); ptx::madc_hi_cc(E[i + 2], a[1], bi);
+_Pragma("unroll")
+                for (int j = 3; j < N; j += 2) { ptx::madc_lo_cc(E[i + j], a[j], bi); ptx::madc_hi_cc(E[i + j + 1], a[j], bi); }
+                if (i + N + 1 < 2 * N) ptx::addc(E[i + N + 1], E[i + N + 1], 0);
+                ptx::mad_lo_cc(O[i - 1], a[0], bi); ptx::madc_hi_cc(O[i], a[0], bi);
+_Pragma("unroll")
+                for (int j = 2; j < N; j += 2) { ptx::madc_lo_cc(O[i + j - 1], a[j], bi); ptx::madc_hi_cc(O[i + j], a[j], bi); }
+                ptx::addc(O[i + N - 1], O[i + N - 1], 0);
+            }
+        }
+        T[0] = E[0];
+        ptx::add_cc(T[1], E[1], O[0]);
+_Pragma("unroll")
+        for (int k = 2; k < 2 * N - 1; k++) ptx::addc_cc(T[k], E[k], O[k - 1]);
+        ptx::addc(T[2 * N - 1], E[2 * N - 1], O[2 * N - 2]);
+    }
+    // one REDC step's shift: X (even columns, X[0] cancelled) / Y (odd columns) -> Y even, X odd, new top limb t enters
+    SB_HD static void shift_in(uint32_t* X, uint32_t* Y, uint32_t t) {
+        ptx::add_cc(Y[0], Y[0], X[1]);
+_Pragma("unroll")
+        for (int j = 0; j < N - 2; j++) ptx::addc_cc(X[j], X[j + 2], 0);
+        ptx::addc_cc(X[N - 2], t, 0);
+        ptx::addc(X[N - 1], 0, 0);
+    }
+    // T (2N limbs, T < p*R) -> T * R^-1 mod p, canonical.  N^2 wide MACs.
+    SB_HD static Fp redc_wide(const uint32_t* T) {
+        uint32_t E[N], O[N];
+_Pragma("unroll")
+        for (int k = 0; k < N; k++) { E[k] = T[k]; O[k] = 0; }
+        reduce(O, E);
+_Pragma("unroll")
+        for (int i = 1; i < N; i += 2) {
+            shift_in(E, O, T[N + i - 1]); reduce(E, O);
+            if (i + 1 < N) { shift_in(O, E, T[N + i]); reduce(O, E); }
+        }
+        Fp r;
+        ptx::add_cc(r.v[0], E[0], O[1]);
+_Pragma("unroll")
+        for (int i = 1; i < N - 1; i++) ptx::addc_cc(r.v[i], E[i], O[i + 1]);
+        ptx::addc(r.v[N - 1], E[N - 1], T[2 * N - 1]);
+        final_sub(r.v);
+        return r;
+    }
+    // 2N-limb helpers: x -= y (returns borrow mask), x += y, high half += p under mask
+    SB_HD static uint32_t wide_sub(uint32_t* x, const uint32_t* y) {
+        uint32_t bw;
+        ptx::sub_cc(x[0], x[0], y[0]);
+_Pragma("unroll")
+        for (int k = 1; k < 2 * N; k++) ptx::subc_cc(x[k], x[k], y[k]);
+        ptx::subc(bw, 0, 0);
+        return bw;
+    }
+    SB_HD static void wide_add_p_high(uint32_t* x, uint32_t mask) {
+        ptx::add_cc(x[N], x[N], mask & P::p(0));
+_Pragma("unroll")
+        for (int k = 1; k < N - 1; k++) ptx::addc_cc(x[N + k], x[N + k], mask & P::p(k));
+        ptx::addc(x[2 * N - 1], x[2 * N - 1], mask & P::p(N - 1));
+    }
+    // plain N-limb sum without reduction (operands < p, p < 2^(32N-1))
+    SB_HD static void add_noreduce(const Fp& a, const Fp& b, uint32_t* out) {
+        ptx::add_cc(out[0], a.v[0], b.v[0]);
+_Pragma("unroll")
+        for (int k = 1; k < N - 1; k++) ptx::addc_cc(out[k], a.v[k], b.v[k]);
+        ptx::addc(out[N - 1], a.v[N - 1], b.v[N - 1]);
+    }
+
     // x*y + u*v for the hot loop: dual product where the modulus allows it, two multiplies otherwise
     SB_HD static Fp mul2_i(const Fp& x, const Fp& y, const Fp& u, const Fp& v) {
         if constexpr (P::p(N - 1) < 0x55555555u) return mul2(x, y, u, v);

@@ -129,6 +129,9 @@ template <class P> static int check_fp2(const char* name) {
         B A = B::mul(x.a, y.a), Bb = B::mul(x.b, y.b), C = B::mul(B::add(x.a, x.b), B::add(y.a, y.b));
         B c0 = B::sub(A, Bb), c1 = B::sub(B::sub(C, A), Bb);
         if (!(m.a == c0) || !(m.b == c1)) { bad++; if (bad < 4) printf("%s fp2 mul mismatch it=%d\n", name, it); }
+        F2 ml = F2::mul_lazy(x, y);
+        if (!(ml == m)) { bad++; if (bad < 4) printf("%s fp2 mul_lazy mismatch it=%d\n", name, it); }
+        { uint32_t T[2 * N]; B::mul_wide(x.a.v, y.b.v, T); B rr = B::redc_wide(T); if (!(rr == B::mul(x.a, y.b))) { bad++; if (bad < 4) printf("%s mul_wide/redc mismatch it=%d\n", name, it); } }
         F2 s = F2::sqr_i(x), s2 = F2::mul_i(x, x);
         if (!(s == s2)) { bad++; if (bad < 4) printf("%s fp2 sqr mismatch it=%d\n", name, it); }
     }
