@@ -60,7 +60,7 @@ struct Groth16Key {
     int shard = 0, n_shards = 1; uint64_t wlo = 0, wcnt = 0, hlo = 0, hcnt = 0;
     uint64_t* d_rowptr = nullptr; uint32_t* d_sig = nullptr; void* d_coef = nullptr; uint64_t nCoef = 0;
     // device work buffers
-    void *dW = nullptr, *dA_T = nullptr, *dB_T = nullptr, *dC_T = nullptr, *dTmp = nullptr, *dWsum = nullptr;
+    void *dW = nullptr, *dA_T = nullptr, *dB_T = nullptr, *dC_T = nullptr, *dTmp = nullptr, *dTmp2 = nullptr, *dTmp3 = nullptr, *dWsum = nullptr;
 };
 
 }  // namespace
@@ -387,7 +387,7 @@ bool modulus_matches(const uint8_t* p, uint32_t n8, int curve, bool scalar_field
 }
 
 void free_key(Groth16Key* k) {
-    for (void* p : {k->tA, k->tB1, k->tB2, k->tC, k->tH, k->dA, k->dB1, k->dB2, k->dC, k->dH, (void*)k->d_rowptr, (void*)k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, k->dTmp, k->dWsum})
+    for (void* p : {k->tA, k->tB1, k->tB2, k->tC, k->tH, k->dA, k->dB1, k->dB2, k->dC, k->dH, (void*)k->d_rowptr, (void*)k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, k->dTmp, k->dTmp2, k->dTmp3, k->dWsum})
         if (p) cudaFree(p);
     delete k;
 }
@@ -800,6 +800,7 @@ static int groth16_load_impl(sb_ctx* c, ZkeySource& src, int shard, int n_shards
     up(&k->d_coef, coef.data(), (size_t)ncoef * 32, (size_t)ncoef * 32);
     up(&k->dW, nullptr, 0, nv * 32);
     up(&k->dA_T, nullptr, 0, n * 32); up(&k->dB_T, nullptr, 0, n * 32); up(&k->dC_T, nullptr, 0, n * 32); up(&k->dTmp, nullptr, 0, n * 32);
+    up(&k->dTmp2, nullptr, 0, n * 32); up(&k->dTmp3, nullptr, 0, n * 32);
     up(&k->dWsum, nullptr, 0, 8 * 80 * 4 * 96);
     if (e != cudaSuccess) { free_key(k); return cuda_fail(c, e, "sb_groth16_load upload"); }
     if (want_precomp(c, wcnt) && want_precomp(c, hcnt)) {
@@ -869,14 +870,23 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     uint8_t ninv[32];
     if (cv == SB_BN254) ninv_bytes<BnFr>(k->power, ninv); else ninv_bytes<BlsFr>(k->power, ninv);
     FrPre pre; rc = get_pre(c, n, ninv, inc, &pre); if (rc) return rc;
-    void* odd[3]; void* bufs[3] = {k->dA_T, k->dB_T, k->dC_T};
-    for (int i = 0; i < 3; i++) {
-        void* r1 = nullptr; void* r2 = nullptr;
-        rc = ntt_dev(c, bufs[i], tmp, n, 1, nullptr, false, &r1); if (rc) return rc;
-        void* other = (r1 == bufs[i]) ? tmp : bufs[i];
-        rc = ntt_dev(c, r1, other, n, 0, &pre, false, &r2); if (rc) return rc;
-        odd[i] = r2;
-        tmp = (r2 == r1) ? other : r1;   // the buffer not holding the result becomes the next scratch
+    // the three transforms run as one batch per pass (A, B, C together: grids fill whole waves)
+    void* odd[3]; void* bufs[3] = {k->dA_T, k->dB_T, k->dC_T}; void* scr[3] = {k->dTmp, k->dTmp2, k->dTmp3};
+    {
+        FrNttTables tbi, tbf;
+        rc = get_ntt_tab(c, k->power, true, &tbi); if (rc) return rc;
+        rc = get_ntt_tab(c, k->power, false, &tbf); if (rc) return rc;
+        int side = 0, launches = 0;
+        rc = fr_ntt_batch(cv, bufs, scr, 3, k->power, &tbi, nullptr, nullptr, c->stream, &side, &launches);      // unscaled inverse
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt_batch");
+        void** src = side ? scr : bufs; void** dst = side ? bufs : scr;
+        int side2 = 0;
+        rc = fr_ntt_batch(cv, src, dst, 3, k->power, &tbf, &pre, nullptr, c->stream, &side2, &launches);         // coset NTT, 1/n folded in
+        if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt_batch");
+        c->launches += launches;
+        void** res = side2 ? dst : src; void** fre = side2 ? src : dst;
+        for (int i = 0; i < 3; i++) odd[i] = res[i];
+        tmp = fre[0];                                     // a buffer that holds no result: output of joinABC
     }
     // joinABC (:320-374) -> plain scalars for the H MSM, written over the remaining scratch buffer
     rc = fr_join_abc(cv, odd[0], odd[1], odd[2], tmp, n, c->stream); c->launches++;

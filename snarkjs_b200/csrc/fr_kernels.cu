@@ -20,6 +20,16 @@ int fr_ntt(int curve, void* a, void* b, int L, const FrNttTables* tb, const FrPr
         return (int)cudaGetLastError();
     })
 }
+int fr_ntt_batch(int curve, void* const* a, void* const* b, int count, int L, const FrNttTables* tb, const FrPre* pre, const void* post_scale,
+                 cudaStream_t stream, int* side, int* launches) {
+    if (count < 1 || count > 4) return -1;
+    FR_DISPATCH(curve, {
+        NttTables<F> t; t.tw_lo = (const F*)tb->tw_lo; t.tw_hi = (const F*)tb->tw_hi; t.h = tb->h; t.wr = (const F*)tb->wr;
+        NttPre<F> p; if (pre) { p.lo = (const F*)pre->lo; p.hi = (const F*)pre->hi; p.h = pre->h; }
+        *side = ntt_run_batch<F>((F* const*)a, (F* const*)b, count, L, t, pre ? &p : nullptr, (const F*)post_scale, stream, launches);
+        return (int)cudaGetLastError();
+    })
+}
 int fr_apply_key(int curve, const void* in, void* out, uint64_t n, const FrPre* t, cudaStream_t stream) {
     FR_DISPATCH(curve, {
         NttPre<F> p; p.lo = (const F*)t->lo; p.hi = (const F*)t->hi; p.h = t->h;
