@@ -65,6 +65,8 @@ struct Groth16Key {
 
 }  // namespace
 
+static constexpr size_t STAGE_BYTES = 8u << 20;
+
 struct sb_ctx {
     int curve = 0, device = 0;
     cudaStream_t stream = nullptr;
@@ -76,6 +78,8 @@ struct sb_ctx {
     cudaStream_t aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // high-priority side streams (tails, NTT chain)
     cudaEvent_t pev[16];                         // pipeline events
     uint8_t* pinned = nullptr;                   // 256 KiB pinned staging (window sums, counters)
+    uint8_t* stage[2] = {nullptr, nullptr};      // 2 x 8 MiB pinned staging for large pageable host buffers
+    cudaEvent_t stage_ev[2];
     MsmLaunchStats stats;
     uint64_t launches = 0;
     DevBuf io[4];
@@ -102,6 +106,53 @@ int cuda_fail(sb_ctx* c, cudaError_t e, const char* where) {
     return fail(c, e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
 #define CU(c, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(c, _e, #call); } while (0)
+
+// Host <-> device copies of caller buffers.  Callers hand us pageable memory (Node Buffers, numpy arrays): the driver's
+// own pageable path runs at 5-10 GB/s, so large transfers are staged through two pinned 8 MiB buffers (CPU memcpy of
+// chunk k+1 overlaps the DMA of chunk k).  Pinned caller memory (bench.py's witness) and small transfers go direct.
+int g_stage_enabled = 0;   // staged copies are validated on the GPU before being switched on by default
+bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+cudaError_t h2d(sb_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return cudaSuccess;
+    if (!g_stage_enabled || bytes < (1u << 20) || !c->stage[0] || !c->stage[1] || host_is_pinned(src))
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    size_t off = 0; int k = 0; cudaError_t e = cudaSuccess;
+    while (off < bytes && e == cudaSuccess) {
+        const int b = k & 1; const size_t n = std::min(STAGE_BYTES, bytes - off);
+        if (k >= 2) e = cudaEventSynchronize(c->stage_ev[b]);
+        if (e != cudaSuccess) break;
+        memcpy(c->stage[b], (const uint8_t*)src + off, n);
+        e = cudaMemcpyAsync((uint8_t*)dst + off, c->stage[b], n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[b], c->stream);
+        off += n; k++;
+    }
+    // the staging buffers may be reused by the next call: make sure their DMAs are done
+    if (e == cudaSuccess) e = cudaEventSynchronize(c->stage_ev[0]);
+    if (e == cudaSuccess && k > 1) e = cudaEventSynchronize(c->stage_ev[1]);
+    return e;
+}
+// synchronous on return (the data is in dst)
+cudaError_t d2h(sb_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return cudaSuccess;
+    if (!g_stage_enabled || bytes < (1u << 20) || !c->stage[0] || !c->stage[1] || host_is_pinned(dst)) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+        return e == cudaSuccess ? cudaStreamSynchronize(c->stream) : e;
+    }
+    size_t off = 0, prev_off = 0, prev_n = 0; int k = 0; cudaError_t e = cudaSuccess;
+    while (off < bytes && e == cudaSuccess) {
+        const int b = k & 1; const size_t n = std::min(STAGE_BYTES, bytes - off);
+        e = cudaMemcpyAsync(c->stage[b], (const uint8_t*)src + off, n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[b], c->stream);
+        if (e == cudaSuccess && k >= 1) { e = cudaEventSynchronize(c->stage_ev[b ^ 1]); if (e == cudaSuccess) memcpy((uint8_t*)dst + prev_off, c->stage[b ^ 1], prev_n); }
+        prev_off = off; prev_n = n; off += n; k++;
+    }
+    if (e == cudaSuccess && k >= 1) { const int b = (k - 1) & 1; e = cudaEventSynchronize(c->stage_ev[b]); if (e == cudaSuccess) memcpy((uint8_t*)dst + prev_off, c->stage[b], prev_n); }
+    return e;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // host Fr helpers, templated on the scalar-field tag
@@ -337,12 +388,12 @@ int msm_host_inputs(sb_ctx* c, int group, const uint8_t* bases, const void* d_ba
         if (!d_bases) {
             void* p = c->io[0].get(n * G.aff_bytes);
             if (!p) return fail(c, SB_ERR_NOMEM, "out of device memory");
-            CU(c, cudaMemcpyAsync(p, bases, n * G.aff_bytes, cudaMemcpyHostToDevice, c->stream));
+            CU(c, h2d(c, p, bases, n * G.aff_bytes));
             d_bases = p;
         }
         uint8_t* d_sc = (uint8_t*)c->io[1].get(n * sbytes);
         if (!d_sc) return fail(c, SB_ERR_NOMEM, "out of device memory");
-        CU(c, cudaMemcpyAsync(d_sc, scalars, n * sbytes, cudaMemcpyHostToDevice, c->stream));
+        CU(c, h2d(c, d_sc, scalars, n * sbytes));
         tick(c, 1);
         prof_begin(c);
         int rc = msm_dev_accumulate(c, G, d_bases, d_sc, sbytes, n, acc.data(), gp, first);
@@ -421,6 +472,7 @@ int sb_create(int curve, int device_id, sb_ctx** out) {
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
       for (auto& st : c->aux) cudaStreamCreateWithPriority(&st, cudaStreamDefault, hi); }
     if (cudaHostAlloc((void**)&c->pinned, 256 * 1024, cudaHostAllocDefault) != cudaSuccess) c->pinned = nullptr;
+    for (int i = 0; i < 2; i++) { if (cudaHostAlloc((void**)&c->stage[i], STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) c->stage[i] = nullptr; cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming); }
     init_generators(c);
     int rc = curve == SB_BN254 ? init_roots<BnFr>(c) : init_roots<BlsFr>(c);
     if (rc == 0 && fr_configure(curve) != 0) rc = SB_ERR_CUDA;
@@ -447,6 +499,7 @@ void sb_destroy(sb_ctx* c) {
     for (auto& e : c->pev) cudaEventDestroy(e);
     for (auto& st : c->aux) { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } }
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < 2; i++) { if (c->stage[i]) cudaFreeHost(c->stage[i]); cudaEventDestroy(c->stage_ev[i]); }
     c->sort_scratch2.release(); for (auto& b : c->bscr) b.release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -546,12 +599,12 @@ int sb_ntt_fr(sb_ctx* c, const uint8_t* in, uint64_t n, int inverse, uint8_t* ou
     void* a = c->io[0].get(n * 32); void* b = c->io[1].get(n * 32);
     if (!a || !b) return fail(c, SB_ERR_NOMEM, "out of device memory");
     tick(c, 0);
-    CU(c, cudaMemcpyAsync(a, in, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, h2d(c, a, in, n * 32));
     tick(c, 1);
     void* res = nullptr;
     int rc = ntt_dev(c, a, b, n, inverse, nullptr, true, &res); if (rc) return rc;
     tick(c, 2);
-    CU(c, cudaMemcpyAsync(out, res, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, d2h(c, out, res, n * 32));
     tick(c, 3);
     CU(c, cudaStreamSynchronize(c->stream));
     c->last_ms[0] = elapsed(c, 0, 3); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2); c->last_ms[3] = elapsed(c, 2, 3);
@@ -575,11 +628,10 @@ int sb_fr_batch_apply_key(sb_ctx* c, const uint8_t* in, uint64_t n, const uint8_
     FrPre pre; int rc = get_pre(c, n, first, inc, &pre); if (rc) return rc;
     void* a = c->io[0].get(n * 32); void* b = c->io[1].get(n * 32);
     if (!a || !b) return fail(c, SB_ERR_NOMEM, "out of device memory");
-    CU(c, cudaMemcpyAsync(a, in, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, h2d(c, a, in, n * 32));
     rc = fr_apply_key(c->curve, a, b, n, &pre, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_apply_key");
-    CU(c, cudaMemcpyAsync(out, b, n * 32, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, d2h(c, out, b, n * 32));
     return 0;
 }
 static int convert_impl(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, int to_mont) {
@@ -588,11 +640,10 @@ static int convert_impl(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, 
     cudaSetDevice(c->device);
     void* a = c->io[0].get(n * 32); void* b = c->io[1].get(n * 32);
     if (!a || !b) return fail(c, SB_ERR_NOMEM, "out of device memory");
-    CU(c, cudaMemcpyAsync(a, in, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, h2d(c, a, in, n * 32));
     int rc = fr_convert(c->curve, a, b, n, to_mont, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_convert");
-    CU(c, cudaMemcpyAsync(out, b, n * 32, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, d2h(c, out, b, n * 32));
     return 0;
 }
 int sb_fr_batch_to_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { return convert_impl(c, in, n, out, 1); }
@@ -604,13 +655,12 @@ int sb_qap_join_abc(sb_ctx* c, const uint8_t* a, const uint8_t* b, const uint8_t
     cudaSetDevice(c->device);
     void* da = c->io[0].get(n * 32); void* db = c->io[1].get(n * 32); void* dc = c->io[2].get(n * 32); void* dout = c->io[3].get(n * 32);
     if (!da || !db || !dc || !dout) return fail(c, SB_ERR_NOMEM, "out of device memory");
-    CU(c, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(dc, cc, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, h2d(c, da, a, n * 32));
+    CU(c, h2d(c, db, b, n * 32));
+    CU(c, h2d(c, dc, cc, n * 32));
     int rc = fr_join_abc(c->curve, da, db, dc, dout, n, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_join_abc");
-    CU(c, cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, d2h(c, out, dout, n * 32));
     return 0;
 }
 
@@ -624,6 +674,7 @@ int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) {
 }
 
 int sb_set_tuning(int key, int value) {
+    if (key == 8) { g_stage_enabled = value; return 0; }                                                      // pinned staging of pageable buffers
     if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
     if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
 }
@@ -637,8 +688,7 @@ int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out)
     if (!d) return fail(c, SB_ERR_NOMEM, "out of device memory");
     int rc = G.gen_points(group == SB_G1 ? c->gen1.data() : c->gen2.data(), seed, n, d, c->stream); c->launches++;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "gen_points");
-    CU(c, cudaMemcpyAsync(out, d, n * G.aff_bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, d2h(c, out, d, n * G.aff_bytes));
     return 0;
 }
 int sb_generator(sb_ctx* c, int group, uint8_t* out) {
@@ -649,8 +699,8 @@ int sb_generator(sb_ctx* c, int group, uint8_t* out) {
 
 void* sb_dev_alloc(sb_ctx* c, uint64_t bytes) { if (!c) return nullptr; cudaSetDevice(c->device); void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; return p; }
 int sb_dev_free(sb_ctx* c, void* p) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaFree(p)); return 0; }
-int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
-int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, h2d(c, dst, src, bytes)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, d2h(c, dst, src, bytes)); return 0; }
 
 // ---------------------------------------------------------------------------------------------------- Groth16
 // A zkey comes either as a memory image (z != nullptr) or as a file streamed section by section: the small sections
@@ -857,7 +907,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     const int cv = c->curve;
     int rc;
     tick(c, 0);
-    if (witness) CU(c, cudaMemcpyAsync(k->dW, witness, nv * 32, cudaMemcpyHostToDevice, c->stream));
+    if (witness) CU(c, h2d(c, k->dW, witness, nv * 32));
     tick(c, 1);
     prof_begin(c);
     void* tmp = k->dTmp;
