@@ -472,3 +472,35 @@ def test_chunked_paths(bn, golden):
         pk.release()
     finally:
         bn.lib.sb_set_tuning(6, 0)
+
+
+def test_staged_host_copies(bn, golden):
+    """sb_set_tuning(8, 1): pageable caller buffers >= 1 MiB go through the pinned double-buffered staging path (both
+    directions, odd sizes, several chunks); results are unchanged."""
+    from snarkjs_b200 import groth16, synth
+    x = rand_fr(71, (1 << 19) + 0)                       # 16 MiB: two 8 MiB chunks exactly
+    y = rand_fr(72, 300001)                              # 9.2 MiB: one full chunk + remainder
+    want_fft = O.fr_fft(BN, x)
+    want_conv = O.batch_convert(O.F_BN_FR, True, y)
+    n = 40000
+    bases = O.gen_points(BN, 1, 73, n)                   # 2.4 MiB of bases, 1.2 MiB of scalars
+    sc = rand_fr(74, n)
+    want_msm = O.g_to_affine(BN, 1, O.multiexp_affine(BN, 1, bases, sc))
+    L = 16
+    zkey = synth.synth_groth16_zkey(bn, L, seed=11)
+    w = synth.chain_witness(bn.r, L)                     # 2 MiB pageable witness
+    ci = O.CURVES[BN]
+    r, s = ci.fr_to_mont(3), ci.fr_to_mont(4)
+    pk = groth16.ProvingKey(zkey, curve=bn)
+    want_proof = pk.prove_raw(w, r, s)
+    bn.lib.sb_set_tuning(8, 1)
+    try:
+        assert np.array_equal(bn.Fr.fft(x), want_fft)
+        assert np.array_equal(bn.Fr.batchToMontgomery(y), want_conv)
+        assert bn.G1.toAffine(bn.G1.multiExpAffine(bases, sc)).tobytes() == want_msm
+        assert pk.prove_raw(w, r, s) == want_proof
+        pts = synth.gen_points(bn, 2, 5, 20000)          # 2.5 MiB device -> host
+    finally:
+        bn.lib.sb_set_tuning(8, 0)
+    assert pts.tobytes() == synth.gen_points(bn, 2, 5, 20000).tobytes()
+    pk.release()
