@@ -110,7 +110,7 @@ int cuda_fail(sb_ctx* c, cudaError_t e, const char* where) {
 // Host <-> device copies of caller buffers.  Callers hand us pageable memory (Node Buffers, numpy arrays): the driver's
 // own pageable path runs at 5-10 GB/s, so large transfers are staged through two pinned 8 MiB buffers (CPU memcpy of
 // chunk k+1 overlaps the DMA of chunk k).  Pinned caller memory (bench.py's witness) and small transfers go direct.
-int g_stage_enabled = 0;   // staged copies are validated on the GPU before being switched on by default
+int g_stage_enabled = 1;   // sb_set_tuning(8, 0) falls back to the driver's pageable path
 bool host_is_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
