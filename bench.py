@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 domain of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--witness-like", action="store_true", help="witness distribution of real circuits (SURVEY 8d): 50% zeros, 25% ones, 25% uniform")
     ap.add_argument("--check-oracle", action="store_true", help="also prove the full workload with the CPU oracle and compare proof bytes (minutes)")
     return ap.parse_args()
 
@@ -157,6 +158,10 @@ def run_b200(args):
     pk = groth16.ProvingKey(zkey, curve=curve, shard=rank, n_shards=world)
     t_setup = time.perf_counter() - t0
     wit_np = synth.chain_witness(curve.r, L)
+    if args.witness_like:
+        wl = wit_np.reshape(-1, 32).copy(); kind = np.random.default_rng(7).integers(0, 4, wl.shape[0])
+        wl[kind < 2] = 0; wl[kind == 2] = 0; wl[kind == 2, 0] = 1; wl[0] = 0; wl[0, 0] = 1
+        wit_np = wl.reshape(-1)
     wit = torch.from_numpy(wit_np.copy()).pin_memory()           # pinned host witness: the e2e input
     wptr = wit.data_ptr()
     nwit = wit.numel() // 32
@@ -262,7 +267,7 @@ def run_b200(args):
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "u32x8 (256-bit modular integers, 32-bit limbs)", "data": "synthetic",
         "config": {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{L} (nVars 2^{L}, {2 * ((1 << L) - 3) + 2} QAP coefficients); 4 G1 MSM + 1 G2 MSM of 2^{L} points, 6 NTT of 2^{L}",
-                   "curve": "bn128", "parallelism": f"msm point-range shards x{world}" if world > 1 else "single GPU",
+                   "curve": "bn128", "witness": "witness-like (50% zeros, 25% ones)" if args.witness_like else "uniform field elements (chain circuit)", "parallelism": f"msm point-range shards x{world}" if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (384 MiB of bases + 32 MiB witness per proof vs 126 MB L2)"},
         "e2e": {"value": args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": int(nwit * 32), "d2h_bytes_per_step": int(proof.size),
                 "ms_per_step": dt_e2e / args.steps * 1e3, "api": "sb_groth16_prove (pinned host witness -> affine proof bytes on host)"},
