@@ -506,3 +506,36 @@ def test_staged_host_copies(bn, golden):
       finally:
         bn.lib.sb_set_tuning(8, 1)
     pk.release()
+
+
+def test_table_mode_full_width_scalars_and_bls(bn, bls):
+    """Registered bases (precomputed window tables): arbitrary 256-bit scalars (the reference accepts any value
+    < 2^(8*sScalar)), short scalars, BLS12-381 G1/G2, and the partial/sum-partials exchange API."""
+    import ctypes
+    from snarkjs_b200.curve import _ptr
+    n = 1 << 13
+    rng = np.random.default_rng(99)
+    for curve, cid, grp in ((bn, BN, 1), (bn, BN, 2), (bls, BLS, 1), (bls, BLS, 2)):
+        G = curve.G1 if grp == 1 else curve.G2
+        bases = O.gen_points(cid, grp, 60 + grp, n)
+        h = G.registerBases(bases)
+        full = rng.integers(0, 256, size=n * 32, dtype=np.uint8)            # uniform 256-bit values, most >= r
+        full[:32] = 255
+        got = G.multiExpRegistered(h, full)
+        assert G.toAffine(got).tobytes() == O.g_to_affine(cid, grp, O.multiexp_affine(cid, grp, bases, full)), (cid, grp)
+        short = rng.integers(0, 256, size=n * 5, dtype=np.uint8)             # 5-byte scalars through the table path
+        out = np.empty(G.sJacobian, np.uint8)
+        curve.check(curve.lib.sb_msm_registered(curve.handle, h, 0, _ptr(short), 5, n, _ptr(out)))
+        assert G.toAffine(out).tobytes() == O.g_to_affine(cid, grp, O.multiexp_affine(cid, grp, bases, short)), (cid, grp, "short")
+        # exchange unit: two half-range partials summed on the host == whole
+        pb = curve.lib.sb_msm_partial_bytes(curve.handle, grp)
+        parts = np.empty(2 * pb, np.uint8)
+        half = n // 2
+        sc = rand_fr(61, n, cid)
+        for i in range(2):
+            curve.check(curve.lib.sb_msm_registered_partial(curve.handle, h, i * half, _ptr(sc[i * half * 32:(i + 1) * half * 32]), 32, half,
+                                                            ctypes.c_void_p(parts.ctypes.data + i * pb)))
+        summed = np.empty(G.sJacobian, np.uint8)
+        curve.check(curve.lib.sb_msm_sum_partials(curve.handle, grp, _ptr(parts), 2, _ptr(summed)))
+        assert G.toAffine(summed).tobytes() == O.g_to_affine(cid, grp, O.multiexp_affine(cid, grp, bases, sc)), (cid, grp, "partials")
+        curve.check(curve.lib.sb_bases_release(curve.handle, h))
