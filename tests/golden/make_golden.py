@@ -101,8 +101,19 @@ def groth16_case():
     print("groth16_case: zkey", len(zkey), "wtns", len(wt))
 
 
+def plonk_case():
+    """The reference's PLONK fixture as data: proving key, witness, verification key, public signals and the stored
+    proof.json (kept although it is stale: see oracle/plonk.py header)."""
+    d = f"{REF}/plonk_circuit"
+    out = {name: u8(open(f"{d}/{fn}", "rb").read()) for name, fn in
+           [("zkey", "circuit.zkey"), ("wtns", "witness.wtns"), ("vk_json", "verification_key.json"),
+            ("public_json", "public.json"), ("proof_json", "proof.json")]}
+    np.savez(os.path.join(HERE, "plonk_case.npz"), **out)
+    print("plonk_case:", {k: v.size for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ntt", "msm", "ptau", "groth16"]
+    which = sys.argv[1:] or ["ntt", "msm", "ptau", "groth16", "plonk"]
     if "ntt" in which:
         ntt_goldens()
     if "msm" in which:
@@ -111,3 +122,5 @@ if __name__ == "__main__":
         ptau_goldens()
     if "groth16" in which:
         groth16_case()
+    if "plonk" in which:
+        plonk_case()
