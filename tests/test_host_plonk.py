@@ -1,0 +1,95 @@
+"""CPU: the PLONK control flow (snarkjs_b200/csrc/plonk_flow.h: rounds, Keccak transcript, round-5 scalars) and the
+per-element functions the CUDA kernels call (plonk.cuh), compiled with g++ behind a host backend
+(tests/host/host_plonk.cpp; NTT / MSM borrowed from the oracle) and compared with oracle/plonk.py proof for proof."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import plonk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BLINDERS = [0x2000 + 7919 * i for i in range(11)]
+
+
+@pytest.fixture(scope="module")
+def hostlib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hp") / "libhostplonk.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "host", "host_plonk.cpp"), "-ldl"])
+    lib = ctypes.CDLL(so)
+    lib.hp_plonk_prove.restype = ctypes.c_int
+    lib.hp_plonk_prove.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64,
+                                   ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    lib.hp_keccak256.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    return lib
+
+
+def host_prove(lib, zkey: bytes, wtns: bytes, blinders):
+    ci = orc.CURVES[orc.BN254]
+    _, wit = orc.read_wtns(wtns)
+    out = ctypes.create_string_buffer(9 * 64 + 6 * 32)
+    err = ctypes.create_string_buffer(256)
+    bl = b"".join(ci.fr_to_mont(b) for b in blinders)
+    rc = lib.hp_plonk_prove(orc.build().encode(), zkey, len(zkey), wit, len(wit) // 32, bl, out, err, 256)
+    return rc, err.value.decode(), out.raw
+
+
+def proof_from_bytes(raw: bytes):
+    ci = orc.CURVES[orc.BN254]
+    names = ["A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw"]
+    proof = {k: plonk._g1_obj(ci.g1_from_affine_bytes(raw[64 * i:64 * i + 64])) for i, k in enumerate(names)}
+    for i, k in enumerate(["eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"]):
+        proof[k] = str(ci.fr_from_mont(raw[576 + 32 * i:608 + 32 * i]))
+    proof["protocol"] = "plonk"
+    proof["curve"] = "bn128"
+    return proof
+
+
+def test_host_keccak(hostlib):
+    for msg in (b"", b"abc", b"x" * 135, b"y" * 136, b"z" * 500):
+        out = ctypes.create_string_buffer(32)
+        hostlib.hp_keccak256(msg, len(msg), out)
+        assert out.raw == plonk.keccak256(msg)
+
+
+def test_host_flow_reference_fixture(hostlib, golden):
+    g = golden("plonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, _ = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    assert proof_from_bytes(raw) == want
+
+
+@pytest.mark.parametrize("n_gates", [13, 120, 500])
+def test_host_flow_synthetic(hostlib, n_gates):
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(n_gates)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=0xABCDEF0123456789)
+    wtns = plonk.wtns_bytes(wit)
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    got = proof_from_bytes(raw)
+    assert got == want
+    assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, got)
+
+
+def test_host_flow_errors(hostlib):
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(40)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=12345)
+    bad = list(wit)
+    bad[4] = (bad[4] + 1) % orc.P_BN_R
+    rc, err, _ = host_prove(hostlib, zkey, plonk.wtns_bytes(bad), BLINDERS)
+    assert rc != 0 and ("Copy constraints does not match" in err or "not divisible" in err)
+    rc, err, _ = host_prove(hostlib, zkey, plonk.wtns_bytes(wit[:-1]), BLINDERS)
+    assert rc != 0 and err.startswith("Invalid witness length. Circuit: ")
+    g16 = bytearray(zkey)
+    # protocol id lives in section 1: flip it to groth16
+    idx = bytes(g16).index(b"\x01\x00\x00\x00\x04\x00\x00\x00\x00\x00\x00\x00\x02\x00\x00\x00")
+    g16[idx + 12] = 1
+    rc, err, _ = host_prove(hostlib, bytes(g16), plonk.wtns_bytes(wit), BLINDERS)
+    assert rc != 0 and err == "zkey file is not plonk"
