@@ -98,6 +98,22 @@ int sb_groth16_prove_wtns(sb_ctx* ctx, uint64_t handle, const uint8_t* wtns, uin
  * (no host->device copy): the device-resident timing bench.py reports as `value`. */
 int sb_groth16_prove_resident(sb_ctx* ctx, uint64_t handle, const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
 int sb_groth16_release(sb_ctx* ctx, uint64_t handle);
+/* ---- PLONK (src/plonk_prove.js:47-889), next-tier path per SURVEY §8f rank 3 ----------------------------------
+ * sb_plonk_load: a PLONK zkey (protocol id 2, sections 2-14: src/zkey_utils.js:261-299, src/plonk_constants.js) goes to
+ *   HBM once: selector / sigma / Lagrange polynomials in coefficient and 4n-evaluation form, wire maps, additions, and the
+ *   PTau bases (section 14) with their MSM window tables.  Error "zkey file is not plonk" as plonk_prove.js:58-60.
+ * sb_plonk_prove: witness = section 2 of the .wtns file (plain LE, nVars - nAdditions elements, plonk_prove.js:66-68);
+ *   blinders = b_1..b_11 as 11 Montgomery field elements (the reference draws them with Fr.random(), :246-249);
+ *   proof_out = A B C Z T1 T2 T3 Wxi Wxiw (affine Montgomery, 2*n8q bytes each) then eval_a eval_b eval_c eval_s1
+ *   eval_s2 eval_zw (Montgomery, 32 bytes each): sb_plonk_proof_bytes().  Errors carry the reference's texts:
+ *   "Invalid witness length. Circuit: N, witness: M, A", "Copy constraints does not match" (:436-438),
+ *   "Polynomial is not divisible" (polynomial.js:608, 653), "T Polynomial is not well calculated" (:648-650). */
+int sb_plonk_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handle);
+int sb_plonk_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions);
+uint32_t sb_plonk_proof_bytes(sb_ctx* ctx);
+int sb_plonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,
+                   uint8_t* proof_out);
+int sb_plonk_release(sb_ctx* ctx, uint64_t handle);
 /* multi-GPU: this rank proves with its shard [shard, n_shards) of every MSM and returns the five un-normalised
  * MSM partials (A, B1, C, H in G1; B2 in G2) instead of a proof; the ranks exchange them (NCCL all-gather) and any
  * rank finishes with sb_groth16_finish. */

@@ -65,6 +65,8 @@ struct Groth16Key {
 
 }  // namespace
 
+namespace { struct PlonkKeyDev; void plonk_free_key(PlonkKeyDev*); }   // api_plonk.inl
+
 static constexpr size_t STAGE_BYTES = 8u << 20;
 
 struct sb_ctx {
@@ -89,6 +91,7 @@ struct sb_ctx {
     std::vector<PreTab*> pre_cache;
     std::vector<BaseSet> bases;
     std::vector<Groth16Key*> keys;
+    std::vector<PlonkKeyDev*> plonk_keys;
     cudaEvent_t ev[8];
     float last_ms[8] = {0};
     int fr_s = 0, fr_bits = 254;
@@ -486,6 +489,7 @@ void sb_destroy(sb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto* k : c->keys) if (k) free_key(k);
+    for (auto* k : c->plonk_keys) if (k) plonk_free_key(k);
     for (auto& b : c->bases) { if (b.d) cudaFree(b.d); if (b.table) cudaFree(b.table); }
     for (auto* t : c->pre_cache) { t->lo.release(); t->hi.release(); delete t; }
     for (auto& kv : c->ntt_fwd) { kv.second.lo.release(); kv.second.hi.release(); }
@@ -1194,6 +1198,40 @@ int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen
     uint32_t nw; memcpy(&nw, hd + 4 + n8, 4);
     if (secs[2].len != (uint64_t)nw * n8) return fail(c, SB_ERR_FORMAT, "Invalid witness section size");
     return sb_groth16_prove(c, h, w + secs[2].pos, nw, r, s, proof);
+}
+
+}  // extern "C"
+
+// ================================================================================================================
+// PLONK (src/plonk_prove.js) — templates live outside the extern "C" block
+#include "api_plonk.inl"
+
+extern "C" {
+
+int sb_plonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle) {
+    if (!c || !zkey || !handle) return SB_ERR_ARG;
+    cudaSetDevice(c->device);
+    return c->curve == SB_BN254 ? plonk_load_impl<BnFr>(c, zkey, len, handle) : plonk_load_impl<BlsFr>(c, zkey, len, handle);
+}
+static PlonkKeyDev* get_plonk_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->plonk_keys.size()) ? c->plonk_keys[h - 1] : nullptr; }
+int sb_plonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) {
+    PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
+    if (n_vars) *n_vars = k->z.nVars; if (n_public) *n_public = k->z.nPublic; if (domain_size) *domain_size = k->z.n; if (n_additions) *n_additions = k->z.nAdditions;
+    return 0;
+}
+uint32_t sb_plonk_proof_bytes(sb_ctx* c) { return c ? 9 * c->g1.aff_bytes + 6 * 32 : 0; }
+int sb_plonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders, uint8_t* proof) {
+    PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
+    if (!witness || !blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
+    cudaSetDevice(c->device);
+    return c->curve == SB_BN254 ? plonk_prove_impl<BnFq, BnFr>(c, k, witness, n_witness, blinders, proof)
+                                : plonk_prove_impl<BlsFq, BlsFr>(c, k, witness, n_witness, blinders, proof);
+}
+int sb_plonk_release(sb_ctx* c, uint64_t h) {
+    PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
+    cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
+    plonk_free_key(k); c->plonk_keys[h - 1] = nullptr;
+    return 0;
 }
 
 }  // extern "C"

@@ -199,7 +199,8 @@ static constexpr int PLONK_PAD = 8;
 //   int quotient(const F* f_or_null, const PlonkLinIn*, const PlonkLin<F>*, uint64_t n, uint64_t len, uint64_t m, const F& sub0,
 //                const PlonkPow<F>& pw, const PlonkPow<F>& ipw, F* g, F* P, F* q_plain); // f / (X - b) -> plain scalars
 //   int commit_plain(const F* scal_plain, uint64_t len, uint8_t* affine);
-//   int error(int code, const char* msg);
+// Returns 0, a positive code for the reference's own errors (2 witness length, 3 copy constraints, 4 divisibility; err holds
+// the reference's message) or the backend's negative code.
 template <class PQ, class PR, class B>
 int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w, const uint8_t* witness_plain, uint64_t n_witness,
                      const uint8_t* blinders_mont /*11 x 32*/, uint8_t* proof_out, std::string& err) {
@@ -208,7 +209,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
     const uint32_t aff = k.aff_bytes;
     if (n_witness != (uint64_t)k.nVars - k.nAdditions) {                                             // plonk_prove.js:66-68
         err = "Invalid witness length. Circuit: " + std::to_string(k.nVars) + ", witness: " + std::to_string(n_witness) + ", " + std::to_string(k.nAdditions);
-        return -2;
+        return 2;
     }
     PlonkRound<F> r;
     r.b[0] = F::zero();
@@ -255,7 +256,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
     r.gamma = tr.challenge();
     {
         int flag = be.z(k, r, w);
-        if (flag) { err = "Copy constraints does not match"; return -3; }                            // :436-438
+        if (flag) { err = "Copy constraints does not match"; return 3; }                            // :436-438
         be.copy(w.num, w.bufZ, n);
         F* res = be.ntt(w.num, w.den, n, true);
         be.zero(w.cZ + n, PLONK_PAD); be.copy(w.cZ, res, n);
@@ -275,8 +276,8 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
         F* ct = be.ntt(w.T, w.s4a, 4 * n, true);
         F* ctz = be.ntt(w.Tz, w.s4b, 4 * n, true);
         int flag = be.divzh(n, ct, ctz, w.evA);                                                      // evA is free after t()
-        if (flag & 1) { err = "Polynomial is not divisible"; return -4; }
-        if (flag & 2) { err = "T Polynomial is not well calculated"; return -4; }
+        if (flag & 1) { err = "Polynomial is not divisible"; return 4; }
+        if (flag & 2) { err = "T Polynomial is not well calculated"; return 4; }
         be.zero(w.T1 + n, PLONK_PAD); be.zero(w.T2 + n, PLONK_PAD); be.zero(w.T3 + n, PLONK_PAD);
         be.tsplit(n, w.evA, r.b[10], r.b[11], w.T1, w.T2, w.T3);
         int rc = be.commit(w.T1, n + 1, pt_T1); if (rc) return rc;
@@ -336,10 +337,10 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
         in.S1 = k.s_coef[0]; in.S2 = k.s_coef[1]; in.S3 = k.s_coef[2];
         in.A = w.cA; in.B = w.cB; in.C = w.cC; in.Z = w.cZ; in.T1 = w.T1; in.T2 = w.T2; in.T3 = w.T3;
         int flag = be.quotient(nullptr, &in, &L, n, 0, n + 6, F::zero(), pxi, ipxi, w.g, w.P, w.scal);
-        if (flag) { err = "Polynomial is not divisible"; return -4; }
+        if (flag) { err = "Polynomial is not divisible"; return 4; }
         int rc = be.commit_plain(w.scal, n + 6, pt_Wxi); if (rc) return rc;
         flag = be.quotient(w.cZ, nullptr, nullptr, n, n + 3, n + 3, ezw, pxiw, ipxiw, w.g, w.P, w.scal);
-        if (flag) { err = "Polynomial is not divisible"; return -4; }
+        if (flag) { err = "Polynomial is not divisible"; return 4; }
         rc = be.commit_plain(w.scal, n + 3, pt_Wxiw); if (rc) return rc;
     }
     return 0;

@@ -1,0 +1,84 @@
+"""GPU parity of the PLONK prover (sb_plonk_load / sb_plonk_prove through the C ABI) against oracle/plonk.py:
+identical proof objects for identical blinders, on the reference's own fixture key and on synthetic structured keys
+(which also verify), with and without MSM window tables, plus the reference's error texts."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BLINDERS = [0x3000 + 104729 * i for i in range(11)]
+
+
+@pytest.fixture(scope="module")
+def env():
+    import snarkjs_b200
+    from oracle import oracle as orc
+    from oracle import plonk as oplonk
+    curve = snarkjs_b200.getCurveFromName("bn128")
+    ci = orc.CURVES[orc.BN254]
+    yield {"sb": snarkjs_b200, "orc": orc, "op": oplonk, "curve": curve, "bl": b"".join(ci.fr_to_mont(b) for b in BLINDERS)}
+    curve.terminate()
+
+
+def test_plonk_reference_fixture(env, golden):
+    g = golden("plonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    pk = env["sb"].plonk.ProvingKey(zkey, env["curve"])
+    try:
+        proof, public = env["sb"].plonk.prove(pk, wtns, env["bl"])
+        want, wpub = env["op"].plonk_prove(zkey, wtns, BLINDERS)
+        assert public == wpub == json.loads(bytes(g["public_json"]))
+        assert proof == want
+        assert env["op"].plonk_verify(json.loads(bytes(g["vk_json"])), public, proof)
+        # a second proof on the same key with other blinders: different proof, still valid
+        p2, _ = env["sb"].plonk.prove(pk, wtns)
+        assert p2 != proof and env["op"].plonk_verify(json.loads(bytes(g["vk_json"])), public, p2)
+    finally:
+        pk.release()
+
+
+@pytest.mark.parametrize("n_gates,structured", [(13, True), (120, True), (1000, True), (4090, True), (16000, False)])
+def test_plonk_synthetic(env, n_gates, structured):
+    """4090 gates -> domain 4096, 4102 PTau points: the MSMs run in table mode; 16000 -> domain 2^14 on unstructured points."""
+    op = env["op"]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(n_gates)
+    zkey = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=0x5EED5EED5EED + n_gates, structured=structured)
+    wtns = op.wtns_bytes(wit)
+    pk = env["sb"].plonk.ProvingKey(zkey, env["curve"])
+    try:
+        assert (pk.nVars, pk.nAdditions) == (n_vars, len(adds))
+        proof, public = env["sb"].plonk.prove(pk, wtns, env["bl"])
+        want, wpub = op.plonk_prove(zkey, wtns, BLINDERS)
+        assert public == wpub
+        assert proof == want
+        if structured and n_gates <= 1000:
+            assert op.plonk_verify(op.plonk_vk(zkey), public, proof)
+        # same key, same inputs -> same bytes (no state leaks between proofs)
+        again, _ = env["sb"].plonk.prove(pk, wtns, env["bl"])
+        assert again == proof
+    finally:
+        pk.release()
+
+
+def test_plonk_errors(env, golden):
+    sb, op, orc = env["sb"], env["op"], env["orc"]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(60)
+    zkey = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=777)
+    pk = sb.plonk.ProvingKey(zkey, env["curve"])
+    try:
+        bad = list(wit)
+        bad[5] = (bad[5] + 1) % orc.P_BN_R
+        with pytest.raises(sb.SbError, match="Copy constraints does not match|Polynomial is not divisible"):
+            sb.plonk.prove(pk, op.wtns_bytes(bad), env["bl"])
+        with pytest.raises(sb.SbError, match=r"Invalid witness length. Circuit: \d+, witness: \d+, \d+"):
+            sb.plonk.prove(pk, op.wtns_bytes(wit[:-1]), env["bl"])
+        # the key still works after the errors
+        proof, public = sb.plonk.prove(pk, op.wtns_bytes(wit), env["bl"])
+        assert proof == op.plonk_prove(zkey, op.wtns_bytes(wit), BLINDERS)[0]
+    finally:
+        pk.release()
+    g16 = bytes(golden("groth16_case.npz")["zkey"])
+    with pytest.raises(sb.SbError, match="zkey file is not plonk"):
+        sb.plonk.ProvingKey(g16, env["curve"])
