@@ -62,6 +62,24 @@ def test_plonk_synthetic(env, n_gates, structured):
         pk.release()
 
 
+def test_plonk_bls12381(env):
+    """BLS12-381: 12-limb base field (transcript, MSM), its own Fr roots; parity with the oracle (no pairing check)."""
+    sb, op, orc = env["sb"], env["op"], env["orc"]
+    ci = orc.CURVES[orc.BLS12_381]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(120, r=ci.r)
+    zkey = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=99991, curve=orc.BLS12_381)
+    wtns = op.wtns_bytes(wit, ci.r)
+    curve = sb.getCurveFromName("bls12381")
+    try:
+        pk = sb.plonk.ProvingKey(zkey, curve)
+        proof, public = sb.plonk.prove(pk, wtns, b"".join(ci.fr_to_mont(b) for b in BLINDERS))
+        pk.release()
+        want, wpub = op.plonk_prove(zkey, wtns, BLINDERS)
+        assert (proof, public) == (want, wpub)
+    finally:
+        curve.terminate()
+
+
 def test_plonk_errors(env, golden):
     sb, op, orc = env["sb"], env["op"], env["orc"]
     gates, adds, n_vars, n_pub, wit = op.chain_gates(60)

@@ -28,24 +28,23 @@ def hostlib(tmp_path_factory):
     return lib
 
 
-def host_prove(lib, zkey: bytes, wtns: bytes, blinders):
-    ci = orc.CURVES[orc.BN254]
+def host_prove(lib, zkey: bytes, wtns: bytes, blinders, ci=orc.CURVES[orc.BN254]):
     _, wit = orc.read_wtns(wtns)
-    out = ctypes.create_string_buffer(9 * 64 + 6 * 32)
+    out = ctypes.create_string_buffer(9 * 2 * ci.n8q + 6 * 32)
     err = ctypes.create_string_buffer(256)
     bl = b"".join(ci.fr_to_mont(b) for b in blinders)
     rc = lib.hp_plonk_prove(orc.build().encode(), zkey, len(zkey), wit, len(wit) // 32, bl, out, err, 256)
     return rc, err.value.decode(), out.raw
 
 
-def proof_from_bytes(raw: bytes):
-    ci = orc.CURVES[orc.BN254]
+def proof_from_bytes(raw: bytes, ci=orc.CURVES[orc.BN254]):
     names = ["A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw"]
-    proof = {k: plonk._g1_obj(ci.g1_from_affine_bytes(raw[64 * i:64 * i + 64])) for i, k in enumerate(names)}
+    sg = 2 * ci.n8q
+    proof = {k: plonk._g1_obj(ci.g1_from_affine_bytes(raw[sg * i:sg * i + sg])) for i, k in enumerate(names)}
     for i, k in enumerate(["eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"]):
-        proof[k] = str(ci.fr_from_mont(raw[576 + 32 * i:608 + 32 * i]))
+        proof[k] = str(ci.fr_from_mont(raw[9 * sg + 32 * i:9 * sg + 32 * i + 32]))
     proof["protocol"] = "plonk"
-    proof["curve"] = "bn128"
+    proof["curve"] = ci.name
     return proof
 
 
@@ -76,6 +75,18 @@ def test_host_flow_synthetic(hostlib, n_gates):
     got = proof_from_bytes(raw)
     assert got == want
     assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, got)
+
+
+def test_host_flow_bls12381(hostlib):
+    """Same flow on BLS12-381 (12-limb base field in the transcript, 255-bit scalar field); no pairing check here."""
+    ci = orc.CURVES[orc.BLS12_381]
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(120, r=ci.r)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=99991, curve=orc.BLS12_381)
+    wtns = plonk.wtns_bytes(wit, ci.r)
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS, ci)
+    assert rc == 0, err
+    want, _ = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    assert proof_from_bytes(raw, ci) == want
 
 
 def test_host_flow_errors(hostlib):
