@@ -1,0 +1,515 @@
+"""oracle/fflonk.py — CPU restatement of snarkjs' fflonk prover and verifier.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+
+What it restates (reference file:line):
+  * fflonkProve                  src/fflonk_prove.js:51-1286 (rounds 1-5, getMontgomeryBatchedInverse :1182-1285)
+  * CPolynomial                  src/polynomial/cpolynomial.js:29-82
+  * Polynomial helpers           src/polynomial/polynomial.js: divByZerofier :617-660, divBy :341-360,
+                                 lagrangePolynomialInterpolation :896-930, zerofierPolynomial :932-948
+  * fflonkVerify                 src/fflonk_verify.js:29-597
+  * the fflonk zkey layout       src/zkey_utils.js:301-339, src/fflonk_constants.js:27-44
+
+Pins (tests/test_oracle_fflonk.py): fflonk_vk(test/fflonk/circuit.zkey) equals the reference's circuit_vk.json; a proof
+made here from the reference's circuit.zkey + witness.wtns verifies against that verification key and public.json, and
+stops verifying when a commitment, an evaluation or the public signal is perturbed.  Prover and verifier restate two
+different reference files.  The reference ships no fflonk proof and draws its blinders at random (:321-324), so the
+prover's bytes are not pinned directly: "partially pinned", as oracle/plonk.py.
+
+Field elements are plain ints in [0, r); bulk NTT / MSM go through the C++ restatement.  BN254 only (pairing).
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from . import oracle as orc
+from .plonk import (Transcript, _add, _blind, _commit, _degree, _evaluate, _fft, _fr_w, _g1, _g1_obj, _g1_valid, _ifft,
+                    _ints_from_mont, _mul, _neg)
+
+EVAL_NAMES = ("ql", "qr", "qm", "qo", "qc", "s1", "s2", "s3", "a", "b", "c", "z", "zw", "t1w", "t2w")
+
+
+# ----------------------------------------------------------------------------- polynomial helpers (int lists)
+def _div_zerofier(c: List[int], n: int, beta: int, r: int) -> List[int]:
+    """polynomial.js:617-660: in-place division by (X^n - beta); the top n coefficients must come out zero."""
+    inv = pow(beta, -1, r)
+    out = list(c)
+    for i in range(min(n, len(out))):
+        out[i] = (-inv * out[i]) % r
+    for i in range(n, len(out)):
+        out[i] = (out[i - n] - out[i]) * inv % r
+        if i > len(out) - n - 1 and out[i]:
+            raise ValueError("Polynomial is not divisible")
+    return out
+
+
+def _padd(a: List[int], b: Sequence[int], r: int, k: int = 1) -> List[int]:
+    """Polynomial.add / sub (k = -1) with the reference's length rule: the result has the longer length."""
+    out = list(a) + [0] * max(0, len(b) - len(a))
+    for i, x in enumerate(b):
+        out[i] = (out[i] + k * x) % r
+    return out
+
+
+def _cpoly(polys: Sequence[Sequence[int]]) -> List[int]:
+    """CPolynomial.getPolynomial (cpolynomial.js:52-72): P_0(X^n) + X P_1(X^n) + ...; power-of-two buffer length."""
+    n = len(polys)
+    degs = [_degree(p) for p in polys]
+    max_degree = max(d * n + j for j, d in enumerate(degs))
+    length = 1 << ((max_degree - 1).bit_length())          # 2 ** (log2(maxDegree - 1) + 1)
+    out = [0] * length
+    for j, p in enumerate(polys):
+        for i in range(min(degs[j] + 1, max_degree)):
+            if i * n + j < length:
+                out[i * n + j] = p[i]
+    return out
+
+
+def _interpolate(xs: Sequence[int], ys: Sequence[int], r: int) -> List[int]:
+    """Polynomial.lagrangePolynomialInterpolation (:896-930); result has len(xs) coefficients."""
+    m = len(xs)
+    res = [0] * m
+    for i in range(m):
+        basis = [1]
+        for j in range(m):
+            if j == i:
+                continue
+            nxt = [0] * (len(basis) + 1)                   # basis * (X - xs[j])
+            for k, c in enumerate(basis):
+                nxt[k] = (nxt[k] - c * xs[j]) % r
+                nxt[k + 1] = (nxt[k + 1] + c) % r
+            basis = nxt
+        den = _evaluate(basis, xs[i], r)
+        f = ys[i] * pow(den, -1, r) % r
+        for k, c in enumerate(basis):
+            res[k] = (res[k] + c * f) % r
+    return res
+
+
+def _zerofier(xs: Sequence[int], r: int) -> List[int]:
+    p = [1]
+    for x in xs:
+        nxt = [0] * (len(p) + 1)
+        for k, c in enumerate(p):
+            nxt[k] = (nxt[k] - c * x) % r
+            nxt[k + 1] = (nxt[k + 1] + c) % r
+        p = nxt
+    return p
+
+
+# ----------------------------------------------------------------------------- zkey
+def read_fflonk_zkey(zkey) -> Dict:
+    data, secs = orc.read_binfile(zkey, "zkey", 2)
+    zk = orc.read_zkey_header(data, secs)
+    if zk["protocol"] != "fflonk":
+        raise ValueError("zkey file is not fflonk")                                  # fflonk_prove.js:71-73
+    zk["ci"] = orc.curve_from_q(zk["q"])
+    zk["data"], zk["secs"] = data, secs
+    return zk
+
+
+def fflonk_vk(zkey) -> Dict:
+    """src/zkey_export_verificationkey.js (fflonk branch)."""
+    zk = read_fflonk_zkey(zkey)
+    ci = zk["ci"]
+    x2 = ci.g2_from_affine_bytes(zk["X_2"])
+    vk = {"protocol": "fflonk", "curve": ci.name, "nPublic": zk["nPublic"], "power": zk["power"],
+          "k1": str(ci.fr_from_mont(zk["k1"])), "k2": str(ci.fr_from_mont(zk["k2"])),
+          "w": str(_fr_w(ci, zk["power"]))}
+    for name in ("w3", "w4", "w8", "wr"):
+        vk[name] = str(ci.fr_from_mont(zk[name]))
+    vk["X_2"] = [[str(x2[0][0]), str(x2[0][1])], [str(x2[1][0]), str(x2[1][1])], ["1", "0"]]
+    vk["C0"] = _g1_obj(ci.g1_from_affine_bytes(zk["C0"]))
+    return vk
+
+
+# ----------------------------------------------------------------------------- shared: roots of the opening sets
+def _roots(r: int, xi_seed: int, w3: int, w4: int, w8: int, wr: int):
+    """fflonk_prove.js:843-897 / fflonk_verify.js:246-300"""
+    seed2 = xi_seed * xi_seed % r
+    h0 = seed2 * xi_seed % r
+    S0 = [h0 * pow(w8, i, r) % r for i in range(8)]
+    h1 = h0 * h0 % r
+    S1 = [h1 * pow(w4, i, r) % r for i in range(4)]
+    h2 = h1 * seed2 % r
+    S2 = [h2, h2 * w3 % r, h2 * w3 % r * w3 % r]
+    h3 = h2 * wr % r
+    S2p = [h3, h3 * w3 % r, h3 * w3 % r * w3 % r]
+    xi = h2 * h2 % r * h2 % r
+    return S0, S1, S2, S2p, xi
+
+
+# ----------------------------------------------------------------------------- prover
+def fflonk_prove(zkey, wtns, blinders: Sequence[int], return_parts: bool = False):
+    """src/fflonk_prove.js:51-267 with b[1..9] = blinders[0..8] as field values (the reference draws Fr.random(), :321-324).
+    b1..b6 enter as *raw Montgomery bytes written into the plain evaluation buffers* (:375-380), i.e. the evaluation is
+    b*R mod r; b7..b9 are used as field elements."""
+    zk = read_fflonk_zkey(zkey)
+    ci: orc.CurveInfo = zk["ci"]
+    r = ci.r
+    data, secs = zk["data"], zk["secs"]
+    wh, wbytes = orc.read_wtns(wtns)
+    if wh["q"] != zk["r"]:
+        raise ValueError("Curve of the witness does not match the curve of the proving key")
+    n_vars, n_add, n_pub, n, n_cons, power = zk["nVars"], zk["nAdditions"], zk["nPublic"], zk["domainSize"], zk["nConstraints"], zk["power"]
+    if wh["nWitness"] != n_vars - n_add:
+        raise ValueError(f"Invalid witness length. Circuit: {n_vars}, witness: {wh['nWitness']}, {n_add}")
+    b = [None] + [int(x) % r for x in blinders]
+    assert len(b) == 10
+    k1, k2 = ci.fr_from_mont(zk["k1"]), ci.fr_from_mont(zk["k2"])
+    w3, w4, w8, wr = (ci.fr_from_mont(zk[k]) for k in ("w3", "w4", "w8", "wr"))
+    wn = _fr_w(ci, power)
+
+    wit = [int.from_bytes(wbytes[i:i + 32], "little") for i in range(0, len(wbytes), 32)]
+    wit[0] = 0
+    add_sec = bytes(orc.section(data, secs, 3))
+    internal: List[int] = []
+    n_wit = n_vars - n_add
+
+    def get_witness(idx):
+        if idx < n_wit:
+            return wit[idx]
+        if idx < n_vars:
+            return internal[idx - n_wit]
+        return 0
+
+    for i in range(n_add):
+        s1, s2 = struct.unpack_from("<II", add_sec, i * 72)
+        f1 = ci.fr_from_mont(add_sec[i * 72 + 8:i * 72 + 40])
+        f2 = ci.fr_from_mont(add_sec[i * 72 + 40:i * 72 + 72])
+        internal.append((f1 * get_witness(s1) + f2 * get_witness(s2)) % r)
+
+    def sec_ints(sid, first_fe, count):
+        s = orc.section(data, secs, sid)
+        return _ints_from_mont(ci, bytes(s[first_fe * 32:(first_fe + count) * 32]))
+
+    sigma_coef = [sec_ints(12 + k, 0, n) for k in range(3)]
+    sigma_ev = [sec_ints(12 + k, n, 4 * n) for k in range(3)]
+    ptau = bytes(orc.section(data, secs, 16))
+    ptau += bytes(16 * n * 2 * ci.n8q - len(ptau))        # the reference reserves 16n points, zeros past 9n + 18 (:164-169)
+    c0_point = ci.g1_from_affine_bytes(zk["C0"])
+
+    # ---- round 1 (:319-520)
+    maps = [np.frombuffer(bytes(orc.section(data, secs, sid)), dtype="<u4") for sid in (4, 5, 6)]
+    bufs = [[get_witness(int(m[i])) for i in range(n_cons)] + [0] * (n - n_cons) for m in maps]
+    for j in range(3):                                                               # :375-380
+        bufs[j][n - 2] = b[2 * j + 1] * ci.Rr % r
+        bufs[j][n - 1] = b[2 * j + 2] * ci.Rr % r
+    bufA, bufB, bufC = bufs
+    pA, pB, pC = _ifft(ci, bufA), _ifft(ci, bufB), _ifft(ci, bufC)
+    evA, evB, evC = (_fft(ci, c + [0] * (3 * n)) for c in (pA, pB, pC))
+    q_ev = {name: sec_ints(sid, n, 4 * n) for name, sid in (("QL", 7), ("QR", 8), ("QM", 9), ("QO", 10), ("QC", 11))}
+    lag_ev = [sec_ints(15, 5 * j * n + n, 4 * n) for j in range(max(n_pub, 1))]
+    T0 = [0] * (4 * n)
+    for i in range(4 * n):
+        a_, b_, c_ = evA[i], evB[i], evC[i]
+        pi = 0
+        for j in range(n_pub):
+            pi = (pi - lag_ev[j][i] * bufA[j]) % r
+        T0[i] = (a_ * q_ev["QL"][i] + b_ * q_ev["QR"][i] + a_ * b_ % r * q_ev["QM"][i] + c_ * q_ev["QO"][i] + q_ev["QC"][i] + pi) % r
+    pT0 = _div_zerofier(_ifft(ci, T0), n, 1, r)
+    if _degree(pT0) >= 2 * n - 2:
+        raise ValueError("T0 Polynomial is not well calculated")
+    C1 = _cpoly([pA, pB, pC, pT0])
+    if _degree(C1) >= 8 * n - 8:
+        raise ValueError("C1 Polynomial is not well calculated")
+    pts = {"C1": _commit(ci, ptau, C1)}
+
+    # ---- round 2 (:522-830)
+    t = Transcript(ci)
+    t.add_pol(c0_point)
+    for i in range(n_pub):
+        t.add_scalar(bufA[i])
+    t.add_pol(pts["C1"])
+    beta = t.challenge()
+    t.reset(); t.add_scalar(beta)
+    gamma = t.challenge()
+    num = [0] * n
+    den = [0] * n
+    num[0] = den[0] = 1
+    w = 1
+    for i in range(n):
+        betaw = beta * w % r
+        nn = (bufA[i] + betaw + gamma) * ((bufB[i] + k1 * betaw + gamma) * (bufC[i] + k2 * betaw + gamma) % r) % r
+        dd = (bufA[i] + beta * sigma_ev[0][4 * i] + gamma) * ((bufB[i] + beta * sigma_ev[1][4 * i] + gamma)
+                                                              * (bufC[i] + beta * sigma_ev[2][4 * i] + gamma) % r) % r
+        num[(i + 1) % n] = num[i] * nn % r
+        den[(i + 1) % n] = den[i] * dd % r
+        w = w * wn % r
+    bufZ = [num[i] * pow(den[i], -1, r) % r for i in range(n)]
+    if bufZ[0] != 1:
+        raise ValueError("Copy constraints does not match")
+    cZ = _ifft(ci, bufZ)
+    evZ = _fft(ci, cZ + [0] * (3 * n))
+    pZ = _blind(cZ, [b[9], b[8], b[7]], r)
+    if _degree(pZ) >= n + 3:
+        raise ValueError("Z Polynomial is not well calculated")
+    # T1 (:667-718) on the 2n domain
+    w2n = _fr_w(ci, power + 1)
+    T1 = [0] * (2 * n)
+    T1z = [0] * (2 * n)
+    om = 1
+    for i in range(2 * n):
+        zp = (b[7] * om % r * om + b[8] * om + b[9]) % r
+        l1 = lag_ev[0][2 * i]
+        T1[i] = (evZ[2 * i] - 1) * l1 % r
+        T1z[i] = zp * l1 % r
+        om = om * w2n % r
+    pT1 = _padd(_div_zerofier(_ifft(ci, T1), n, 1, r), _ifft(ci, T1z), r)
+    if _degree(pT1) >= n + 2:
+        raise ValueError("T1 Polynomial is not well calculated")
+    # T2 (:720-815) on the 4n domain
+    w4n = _fr_w(ci, power + 2)
+    T2 = [0] * (4 * n)
+    T2z = [0] * (4 * n)
+    om = 1
+    for i in range(4 * n):
+        omW = om * wn % r
+        zp = (b[7] * om % r * om + b[8] * om + b[9]) % r
+        zWp = (b[7] * omW % r * omW + b[8] * omW + b[9]) % r
+        a_, b_, c_ = evA[i], evB[i], evC[i]
+        betaX = beta * om % r
+        e1c = (a_ + betaX + gamma) * (b_ + betaX * k1 + gamma) % r * (c_ + betaX * k2 + gamma) % r
+        e2c = (a_ + beta * sigma_ev[0][i] + gamma) * (b_ + beta * sigma_ev[1][i] + gamma) % r * (c_ + beta * sigma_ev[2][i] + gamma) % r
+        T2[i] = (e1c * evZ[i] - e2c * evZ[(i + 4) % (4 * n)]) % r
+        T2z[i] = (e1c * zp - e2c * zWp) % r
+        om = om * w4n % r
+    pT2 = _padd(_div_zerofier(_ifft(ci, T2), n, 1, r), _ifft(ci, T2z), r)
+    if _degree(pT2) >= 3 * n:
+        raise ValueError("T2 Polynomial is not well calculated")
+    C2 = _cpoly([pZ, pT1, pT2])
+    if _degree(C2) >= 9 * n:
+        raise ValueError("C2 Polynomial is not well calculated")
+    pts["C2"] = _commit(ci, ptau, C2)
+
+    # ---- round 3 (:832-931)
+    t.reset(); t.add_scalar(gamma); t.add_pol(pts["C2"])
+    xi_seed = t.challenge()
+    S0, S1, S2, S2p, xi = _roots(r, xi_seed, w3, w4, w8, wr)
+    q_coef = {name: sec_ints(sid, 0, n) for name, sid in (("ql", 7), ("qr", 8), ("qm", 9), ("qo", 10), ("qc", 11))}
+    ev: Dict[str, int] = {k: _evaluate(q_coef[k], xi, r) for k in ("ql", "qr", "qm", "qo", "qc")}
+    ev["s1"], ev["s2"], ev["s3"] = (_evaluate(sigma_coef[k], xi, r) for k in range(3))
+    ev["a"], ev["b"], ev["c"] = _evaluate(pA, xi, r), _evaluate(pB, xi, r), _evaluate(pC, xi, r)
+    ev["z"] = _evaluate(pZ, xi, r)
+    xiw = xi * wn % r
+    ev["zw"], ev["t1w"], ev["t2w"] = _evaluate(pZ, xiw, r), _evaluate(pT1, xiw, r), _evaluate(pT2, xiw, r)
+
+    # ---- round 4 (:933-1057)
+    t.reset(); t.add_scalar(xi_seed)
+    for k in EVAL_NAMES:
+        t.add_scalar(ev[k])
+    alpha = t.challenge()
+    C0 = sec_ints(17, 0, 8 * n)
+    R0 = _interpolate(S0, [_evaluate(C0, x, r) for x in S0], r)
+    R1 = _interpolate(S1, [_evaluate(C1, x, r) for x in S1], r)
+    R2 = _interpolate(S2 + S2p, [_evaluate(C2, x, r) for x in S2 + S2p], r)
+    F = _div_zerofier(_padd(C0, R0, r, -1), 8, xi, r)
+    f2 = _div_zerofier([x * alpha % r for x in _padd(C1, R1, r, -1)], 4, xi, r)
+    f3 = [x * alpha % r * alpha % r for x in _padd(C2, R2, r, -1)]
+    f3 = _div_zerofier(_div_zerofier(f3, 3, xi, r), 3, xiw, r)
+    F = _padd(_padd(F, f2, r), f3, r)
+    if _degree(F) >= 9 * n - 6:
+        raise ValueError("F Polynomial is not well calculated")
+    pts["W1"] = _commit(ci, ptau, F)
+
+    # ---- round 5 (:1059-1180)
+    t.reset(); t.add_scalar(alpha); t.add_pol(pts["W1"])
+    y = t.challenge()
+    mulL0 = 1
+    for x in S0:
+        mulL0 = mulL0 * (y - x) % r
+    mulL1 = 1
+    for x in S1:
+        mulL1 = mulL1 * (y - x) % r
+    mulL2 = 1
+    for x in S2 + S2p:
+        mulL2 = mulL2 * (y - x) % r
+    preL0 = mulL1 * mulL2 % r
+    preL1 = alpha * mulL0 % r * mulL2 % r
+    preL2 = alpha * alpha % r * mulL0 % r * mulL1 % r
+    to_inverse: Dict[str, int] = {"denH1": mulL1, "denH2": mulL2}                   # insertion order matters only for the product
+    L = list(C0)
+    L[0] = (L[0] - _evaluate(R0, y, r)) % r
+    L = [x * preL0 % r for x in L]
+    l2 = list(C1)
+    l2[0] = (l2[0] - _evaluate(R1, y, r)) % r
+    l3 = list(C2)
+    l3[0] = (l3[0] - _evaluate(R2, y, r)) % r
+    L = _padd(L, [x * preL1 % r for x in l2], r)
+    L = _padd(L, [x * preL2 % r for x in l3], r)
+    ZT = _zerofier(S0 + S1 + S2 + S2p, r)
+    zty = _evaluate(ZT, y, r)
+    L = _padd(L, [x * zty % r for x in F], r, -1)
+    if _degree(L) >= 9 * n:
+        raise ValueError("L Polynomial is not well calculated")
+    zts2y = pow(_evaluate(_zerofier(S1 + S2 + S2p, r), y, r), -1, r)
+    L = [x * zts2y % r for x in L]
+    # divBy (X - y) (:341-360): synthetic division from the top; the remainder must vanish
+    dA = _degree(L)
+    quo = [0] * len(L)
+    rem = list(L)
+    for i in range(dA - 1, -1, -1):
+        quo[i] = rem[i + 1]
+        rem[i] = (rem[i] + quo[i] * y) % r                 # rem[i+j] -= q_i * divisor[j]; divisor = (-y, 1)
+        rem[i + 1] = 0
+    if _degree(rem) > 0:
+        raise ValueError("Degree of L(X)/(ZTS2(y)(X-y)) remainder should be 0")
+    if _degree(quo) >= 9 * n - 1:
+        raise ValueError("Degree of L(X)/(ZTS2(y)(X-y)) is not correct")
+    pts["W2"] = _commit(ci, ptau, quo)
+
+    # ---- the batched inverse (:1182-1285)
+    to_inverse["zh"] = (pow(xi, n, r) - 1) % r
+    for name, roots in (("LiS0_", S0), ("LiS1_", S1)):
+        ln = len(roots)
+        den1 = ln * pow(roots[0], ln - 2, r) % r
+        for i in range(ln):
+            to_inverse[name + str(i + 1)] = den1 * roots[((ln - 1) * i) % ln] % r * ((y - roots[i]) % r) % r
+    den1 = 3 * S2[0] % r * ((xi - xiw) % r) % r
+    for i in range(3):
+        to_inverse["LiS2_" + str(i + 1)] = den1 * S2[2 * i % 3] % r * ((y - S2[i]) % r) % r
+    den1 = 3 * S2p[0] % r * ((xiw - xi) % r) % r
+    for i in range(3):
+        to_inverse["LiS2_" + str(i + 4)] = den1 * S2p[2 * i % 3] % r * ((y - S2p[i]) % r) % r
+    w = 1
+    for i in range(max(1, n_pub)):
+        to_inverse["Li_" + str(i + 1)] = n * ((xi - w) % r) % r
+        w = w * wn % r
+    acc = 1
+    for v in to_inverse.values():
+        acc = acc * v % r
+    ev["inv"] = pow(acc, -1, r)
+
+    proof = {"polynomials": {k: _g1_obj(pts[k]) for k in ("C1", "C2", "W1", "W2")},
+             "evaluations": {k: str(ev[k]) for k in EVAL_NAMES + ("inv",)},
+             "protocol": "fflonk", "curve": ci.name}
+    public = [str(wit[i]) for i in range(1, n_pub + 1)]
+    if return_parts:
+        return proof, public, {"C1": C1, "C2": C2, "F": F, "W2": quo, "beta": beta, "gamma": gamma, "xi_seed": xi_seed, "alpha": alpha, "y": y}
+    return proof, public
+
+
+# ----------------------------------------------------------------------------- verifier
+def _li_si(roots: Sequence[int], x: int, xi: int, r: int) -> List[int]:
+    """computeLagrangeLiSi, fflonk_verify.js:546-563"""
+    ln = len(roots)
+    num = (pow(x, ln, r) - xi) % r
+    den1 = ln * pow(roots[0], ln - 2, r) % r
+    return [num * pow(den1 * roots[((ln - 1) * i) % ln] % r * ((x - roots[i]) % r) % r, -1, r) % r for i in range(ln)]
+
+
+def _li_s2(S2: Sequence[int], S2p: Sequence[int], x: int, xi0: int, xi1: int, r: int) -> List[int]:
+    """computeLagrangeLiS2, fflonk_verify.js:565-597"""
+    ln = 3
+    num = (pow(x, 6, r) - (xi0 + xi1) * pow(x, ln, r) + xi0 * xi1) % r
+    out = []
+    for roots, d in ((S2, (xi0 - xi1) % r), (S2p, (xi1 - xi0) % r)):
+        den1 = ln * roots[0] % r * d % r
+        for i in range(ln):
+            den = den1 * roots[(ln - 1) * i % ln] % r * ((x - roots[i]) % r) % r
+            out.append(num * pow(den, -1, r) % r)
+    return out
+
+
+def fflonk_verify(vk_json: Dict, public_signals: Sequence, proof_json: Dict) -> bool:
+    """src/fflonk_verify.js:29-137 on JSON-shaped inputs."""
+    ci = orc.CURVES[orc.BN254]
+    if vk_json.get("curve", "bn128") != "bn128":
+        raise NotImplementedError("python pairing is BN254-only")
+    r = ci.r
+    pol = {k: _g1(proof_json["polynomials"][k]) for k in ("C1", "C2", "W1", "W2")}
+    ev = {k: int(proof_json["evaluations"][k]) for k in EVAL_NAMES + ("inv",)}
+    k1, k2, power, n_pub = int(vk_json["k1"]), int(vk_json["k2"]), int(vk_json["power"]), int(vk_json["nPublic"])
+    w, w3, w4, w8, wr = (int(vk_json[k]) for k in ("w", "w3", "w4", "w8", "wr"))
+    x2 = vk_json["X_2"]
+    X_2 = ((int(x2[0][0]), int(x2[0][1])), (int(x2[1][0]), int(x2[1][1])))
+    C0 = _g1(vk_json["C0"])
+    pub = [int(s) for s in public_signals]
+    if len(pub) != n_pub:
+        return False
+    if not all(_g1_valid(p) for p in list(pol.values()) + [C0]):
+        return False
+    if not all(0 <= ev[k] < r for k in EVAL_NAMES) or not all(0 <= s < r for s in pub):
+        return False
+    # challenges (:221-338)
+    t = Transcript(ci)
+    t.add_pol(C0)
+    for s in pub:
+        t.add_scalar(s)
+    t.add_pol(pol["C1"])
+    beta = t.challenge()
+    t.reset(); t.add_scalar(beta)
+    gamma = t.challenge()
+    t.reset(); t.add_scalar(gamma); t.add_pol(pol["C2"])
+    xi_seed = t.challenge()
+    S0, S1, S2, S2p, xi = _roots(r, xi_seed, w3, w4, w8, wr)
+    xiw = xi * w % r
+    n = 1 << power
+    xin = pow(xi, n, r)
+    t.reset(); t.add_scalar(xi_seed)
+    for k in EVAL_NAMES:
+        t.add_scalar(ev[k])
+    alpha = t.challenge()
+    t.reset(); t.add_scalar(alpha); t.add_pol(pol["W1"])
+    y = t.challenge()
+    zh = (xin - 1) % r
+    invzh = pow(zh, -1, r)
+    L = [None]
+    wq = 1
+    for _ in range(max(1, n_pub)):
+        L.append(wq * zh % r * pow(n * (xi - wq) % r, -1, r) % r)
+        wq = wq * w % r
+    pi = 0
+    for i, s in enumerate(pub):
+        pi = (pi - s * L[i + 1]) % r
+    # r0 (:383-410)
+    li = _li_si(S0, y, xi, r)
+    r0 = 0
+    for i in range(8):
+        h = S0[i]
+        c0 = 0
+        for k, name in enumerate(("ql", "qr", "qo", "qm", "qc", "s1", "s2", "s3")):
+            c0 = (c0 + ev[name] * pow(h, k, r)) % r
+        r0 = (r0 + c0 * li[i]) % r
+    # r1 (:412-447)
+    t0 = (ev["ql"] * ev["a"] + ev["qr"] * ev["b"] + ev["qm"] * ev["a"] % r * ev["b"] + ev["qo"] * ev["c"] + ev["qc"] + pi) % r * invzh % r
+    li = _li_si(S1, y, xi, r)
+    r1 = 0
+    for i in range(4):
+        h = S1[i]
+        c1 = (ev["a"] + h * ev["b"] + h * h % r * ev["c"] + h * h % r * h % r * t0) % r
+        r1 = (r1 + c1 * li[i]) % r
+    # r2 (:449-503)
+    t1 = (ev["z"] - 1) * L[1] % r * invzh % r
+    betaxi = beta * xi % r
+    t21 = (ev["a"] + betaxi + gamma) * (ev["b"] + betaxi * k1 + gamma) % r * (ev["c"] + betaxi * k2 + gamma) % r * ev["z"] % r
+    t22 = (ev["a"] + beta * ev["s1"] + gamma) * (ev["b"] + beta * ev["s2"] + gamma) % r * (ev["c"] + beta * ev["s3"] + gamma) % r * ev["zw"] % r
+    t2 = (t21 - t22) * invzh % r
+    li2 = _li_s2(S2, S2p, y, xi, xiw, r)
+    r2 = 0
+    for i in range(3):
+        r2 = (r2 + (ev["z"] + S2[i] * t1 + S2[i] * S2[i] % r * t2) % r * li2[i]) % r
+    for i in range(3):
+        r2 = (r2 + (ev["zw"] + S2p[i] * ev["t1w"] + S2p[i] * S2p[i] % r * ev["t2w"]) % r * li2[i + 3]) % r
+    # F, E, J (:505-544)
+    mulH0 = 1
+    for x in S0:
+        mulH0 = mulH0 * (y - x) % r
+    mulH1 = 1
+    for x in S1:
+        mulH1 = mulH1 * (y - x) % r
+    mulH2 = 1
+    for x in S2 + S2p:
+        mulH2 = mulH2 * (y - x) % r
+    q1 = alpha * mulH0 % r * pow(mulH1, -1, r) % r
+    q2 = alpha * alpha % r * mulH0 % r * pow(mulH2, -1, r) % r
+    Fp = _add(C0, _add(_mul(pol["C1"], q1), _mul(pol["C2"], q2)))
+    E = _mul(ci.g1, (r0 + r1 * q1 + r2 * q2) % r)
+    J = _mul(pol["W1"], mulH0)
+    A1 = _add(_add(_add(Fp, _neg(E)), _neg(J)), _mul(pol["W2"], y))
+    if A1 is None or pol["W2"] is None:
+        return A1 is None and pol["W2"] is None
+    return orc.pairing_product_is_one([(_neg(A1), ci.g2), (pol["W2"], X_2)])

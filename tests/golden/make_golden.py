@@ -112,8 +112,17 @@ def plonk_case():
     print("plonk_case:", {k: v.size for k, v in out.items()})
 
 
+def fflonk_case():
+    """The reference's fflonk fixture as data (test/fflonk): proving key, witness, verification key, public signals."""
+    d = f"{REF}/fflonk"
+    out = {name: u8(open(f"{d}/{fn}", "rb").read()) for name, fn in
+           [("zkey", "circuit.zkey"), ("wtns", "witness.wtns"), ("vk_json", "circuit_vk.json"), ("public_json", "public.json")]}
+    np.savez_compressed(os.path.join(HERE, "fflonk_case.npz"), **out)
+    print("fflonk_case:", {k: v.size for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ntt", "msm", "ptau", "groth16", "plonk"]
+    which = sys.argv[1:] or ["ntt", "msm", "ptau", "groth16", "plonk", "fflonk"]
     if "ntt" in which:
         ntt_goldens()
     if "msm" in which:
@@ -124,3 +133,5 @@ if __name__ == "__main__":
         groth16_case()
     if "plonk" in which:
         plonk_case()
+    if "fflonk" in which:
+        fflonk_case()
