@@ -594,26 +594,27 @@ def plonk_prove(zkey, wtns, blinders: Sequence[int], return_parts: bool = False)
 
 
 # ----------------------------------------------------------------------------- synthetic structured setup
-def chain_gates(n_gates: int, seed: int = 7, r: int = orc.P_BN_R):
+def chain_gates(n_gates: int, seed: int = 7, r: int = orc.P_BN_R, n_pub: int = 1, with_additions: bool = True):
     """A PLONK circuit given directly as gates (the reference derives them from an r1cs, plonk_setup.js:142-299):
-    public output x_m of the chain x_{i+1} = x_i^2 + c, plus linear 'addition' wires y_j = 3 x_j + 7 x_{j+1} and
-    z_j = y_j + 2 y_{j+1} (the shape reduceCoefs emits, plonk_setup.js:176-215), so calculateAdditions is exercised with
-    two dependency levels.  Returns (gates, additions, n_vars, n_public, witness ints for the wtns file).
-    gate = (sl, sr, so, qm, ql, qr, qo, qc) with plain ints."""
-    n_pub = 1
-    n_y = max(2, n_gates // 8)
-    n_z = n_y - 1
+    the chain x_{i+1} = x_i^2 + c with public output x_m (and, for n_pub > 1, x_0, x_1, ... as further public signals),
+    plus linear 'addition' wires y_j = 3 x_j + 7 x_{j+1} and z_j = y_j + 2 y_{j+1} (the shape reduceCoefs emits,
+    plonk_setup.js:176-215), so calculateAdditions is exercised with two dependency levels.
+    Returns (gates, additions, n_vars, n_public, witness ints for the wtns file).
+    gate = (sl, sr, so, qm, ql, qr, qo, qc) with plain ints; the first n_pub gates are the public-input gates
+    (plonk_setup.js:285-297)."""
+    n_y = max(2, n_gates // 8) if with_additions else 0
+    n_z = n_y - 1 if with_additions else 0
     m = n_gates - n_pub - n_y - n_z           # chain multiplications
-    assert m >= n_y + 1
+    assert m >= max(n_y + 1, n_pub)
     cst = (seed * 0x9E3779B97F4A7C15 + 12345) % r
     x = [(seed * 1000003 + 17) % r]
     for _ in range(m):
         x.append((x[-1] * x[-1] + cst) % r)
-    # witness wires: 0 = one, 1 = x_m (public), 2.. = x_0..x_{m-1}
+    # witness wires: 0 = one, 1 = x_m (public), 2..n_pub = x_0.. (public), then the remaining x_i
     wire_x = [2 + i for i in range(m)] + [1]
     wit = [1, x[m]] + x[:m]
     n_wit = len(wit)
-    gates = [(1, 0, 0, 0, 1, 0, 0, 0)]
+    gates = [(s, 0, 0, 0, 1, 0, 0, 0) for s in range(1, n_pub + 1)]
     for i in range(m):
         gates.append((wire_x[i], wire_x[i], wire_x[i + 1], 1, 0, 0, (-1) % r, cst))
     additions = []

@@ -62,6 +62,22 @@ def test_plonk_synthetic(env, n_gates, structured):
         pk.release()
 
 
+@pytest.mark.parametrize("n_gates,n_pub,with_additions", [(29, 3, True), (60, 5, False)])
+def test_plonk_shapes(env, n_gates, n_pub, with_additions):
+    """Several public inputs (PI(X) sums several Lagrange polynomials) and a key without additions."""
+    op = env["op"]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(n_gates, n_pub=n_pub, with_additions=with_additions)
+    zkey = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=31337 + n_gates)
+    wtns = op.wtns_bytes(wit)
+    pk = env["sb"].plonk.ProvingKey(zkey, env["curve"])
+    try:
+        proof, public = env["sb"].plonk.prove(pk, wtns, env["bl"])
+        assert (proof, public) == op.plonk_prove(zkey, wtns, BLINDERS)
+        assert len(public) == n_pub and op.plonk_verify(op.plonk_vk(zkey), public, proof)
+    finally:
+        pk.release()
+
+
 def test_plonk_bls12381(env):
     """BLS12-381: 12-limb base field (transcript, MSM), its own Fr roots; parity with the oracle (no pairing check)."""
     sb, op, orc = env["sb"], env["op"], env["orc"]

@@ -77,6 +77,22 @@ def test_host_flow_synthetic(hostlib, n_gates):
     assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, got)
 
 
+@pytest.mark.parametrize("n_gates,n_pub,with_additions", [(29, 3, True), (60, 5, False), (16, 1, False), (8, 2, False)])
+def test_host_flow_shapes(hostlib, n_gates, n_pub, with_additions):
+    """Several public inputs (PI(X) sums several Lagrange polynomials), no additions at all, a gate count equal to the
+    domain size, and the minimum domain (8)."""
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(n_gates, n_pub=n_pub, with_additions=with_additions)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=31337 + n_gates)
+    wtns = plonk.wtns_bytes(wit)
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    assert len(public) == n_pub
+    got = proof_from_bytes(raw)
+    assert got == want
+    assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, got)
+
+
 def test_host_flow_bls12381(hostlib):
     """Same flow on BLS12-381 (12-limb base field in the transcript, 255-bit scalar field); no pairing check here."""
     ci = orc.CURVES[orc.BLS12_381]
