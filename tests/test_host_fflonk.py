@@ -1,0 +1,71 @@
+"""CPU: the fflonk control flow (snarkjs_b200/csrc/fflonk_flow.h) and the element functions the CUDA kernels call
+(fflonk.cuh, plonk.cuh), compiled with g++ behind a host backend (tests/host/host_fflonk.cpp; NTT / MSM borrowed from
+the oracle) and compared with oracle/fflonk.py proof for proof on the reference's own fflonk fixture key."""
+import ctypes
+import json
+import os
+import subprocess
+
+import pytest
+
+from oracle import fflonk
+from oracle import oracle as orc
+from oracle import plonk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BLINDERS = [0x5000 + 15485863 * i for i in range(9)]
+
+
+@pytest.fixture(scope="module")
+def hostlib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hf") / "libhostfflonk.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "host", "host_fflonk.cpp"), "-ldl"])
+    lib = ctypes.CDLL(so)
+    lib.hp_fflonk_prove.restype = ctypes.c_int
+    lib.hp_fflonk_prove.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64,
+                                    ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    return lib
+
+
+def host_prove(lib, zkey: bytes, wtns: bytes, blinders):
+    ci = orc.CURVES[orc.BN254]
+    _, wit = orc.read_wtns(wtns)
+    out = ctypes.create_string_buffer(4 * 64 + 16 * 32)
+    err = ctypes.create_string_buffer(256)
+    bl = b"".join(ci.fr_to_mont(b) for b in blinders)
+    rc = lib.hp_fflonk_prove(orc.build().encode(), zkey, len(zkey), wit, len(wit) // 32, bl, out, err, 256)
+    return rc, err.value.decode(), out.raw
+
+
+def proof_from_bytes(raw: bytes):
+    ci = orc.CURVES[orc.BN254]
+    pols = {k: plonk._g1_obj(ci.g1_from_affine_bytes(raw[64 * i:64 * i + 64])) for i, k in enumerate(("C1", "C2", "W1", "W2"))}
+    evs = {k: str(ci.fr_from_mont(raw[256 + 32 * i:288 + 32 * i])) for i, k in enumerate(fflonk.EVAL_NAMES + ("inv",))}
+    return {"polynomials": pols, "evaluations": evs, "protocol": "fflonk", "curve": "bn128"}
+
+
+def test_host_fflonk_reference_fixture(hostlib, golden):
+    g = golden("fflonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = fflonk.fflonk_prove(zkey, wtns, BLINDERS)
+    got = proof_from_bytes(raw)
+    assert got == want
+    assert fflonk.fflonk_verify(json.loads(bytes(g["vk_json"])), public, got)
+
+
+def test_host_fflonk_errors(hostlib, golden):
+    g = golden("fflonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    _, w = orc.read_wtns(wtns)
+    wit = [int.from_bytes(w[i:i + 32], "little") for i in range(0, len(w), 32)]
+    bad = list(wit)
+    bad[3] = (bad[3] + 1) % orc.P_BN_R
+    rc, err, _ = host_prove(hostlib, zkey, plonk.wtns_bytes(bad), BLINDERS)
+    assert rc != 0 and ("Copy constraints does not match" in err or "not divisible" in err)
+    rc, err, _ = host_prove(hostlib, zkey, plonk.wtns_bytes(wit[:-1]), BLINDERS)
+    assert rc != 0 and err.startswith("Invalid witness length. Circuit: ")
+    rc, err, _ = host_prove(hostlib, bytes(golden("plonk_case.npz")["zkey"]), wtns, BLINDERS)
+    assert rc != 0 and err == "zkey file is not fflonk"
