@@ -513,3 +513,83 @@ def fflonk_verify(vk_json: Dict, public_signals: Sequence, proof_json: Dict) -> 
     if A1 is None or pol["W2"] is None:
         return A1 is None and pol["W2"] is None
     return orc.pairing_product_is_one([(_neg(A1), ci.g2), (pol["W2"], X_2)])
+
+
+# ----------------------------------------------------------------------------- synthetic structured setup
+def fflonk_setup_synth(gates, additions, n_vars: int, n_public: int, tau: int, structured: bool = True) -> bytes:
+    """The sections src/fflonk_setup.js:211-503 writes (3 additions, 4-6 wire maps, 7-11 QL QR QM QO QC, 12-14 sigmas,
+    15 Lagrange, 16 PTau with 9n + 18 points, 17 C0, 2 header with w3 w4 w8 wr X_2 [C0]_1) for directly-given gates
+    (oracle.plonk.chain_gates) and a KNOWN tau, so that proofs verify.  BN254 only, like the reference's constants
+    (computeW3 :534-542, getOmegaCubicRoot :552-557).  structured=False: pseudo-random PTau points (parity / throughput)."""
+    from .plonk import _g2_times_gen, _mont_from_ints, _tau_powers
+    ci = orc.CURVES[orc.BN254]
+    r = ci.r
+    ng = len(gates)
+    power = max(3, (ng + 2 - 1).bit_length())                                       # fflonk_setup.js:112 (two rows stay free for blinding)
+    n = 1 << power
+    wn = _fr_w(ci, power)
+    k1 = 2
+    while pow(k1, n, r) == 1:
+        k1 += 1
+    k2 = k1 + 1
+    while pow(k2, n, r) == 1 or pow(k2 * pow(k1, -1, r) % r, n, r) == 1:
+        k2 += 1
+    w3 = pow(31624, 3648040478639879203707734290876212514758060733402672390616367364429301415936 // 3, r)   # computeW3 :534-542
+    w4, w8 = _fr_w(ci, 2), _fr_w(ci, 3)
+    wr = pow(467799165886069610036046866799264026481344299079011762026774533774345988080, 1 << (28 - power), r)
+    assert pow(w3, 3, r) == 1 and w3 != 1 and pow(wr, 3, r) == wn
+    secs = [(3, b"".join(struct.pack("<II", a[0], a[1]) + ci.fr_to_mont(a[2]) + ci.fr_to_mont(a[3]) for a in additions))]
+    for pos in range(3):
+        secs.append((4 + pos, np.array([g[pos] for g in gates], dtype="<u4").tobytes()))
+
+    def p4(evals):
+        coef = _ifft(ci, evals)
+        ev4 = orc.fr_fft(ci.id, _mont_from_ints(ci, coef + [0] * (3 * n)), False)
+        return _mont_from_ints(ci, coef) + bytes(ev4), coef
+
+    polys = {}
+    # gate tuple = (sl, sr, so, qm, ql, qr, qo, qc); sections 7..11 hold QL QR QM QO QC
+    for sid, name, pos in ((7, "QL", 4), (8, "QR", 5), (9, "QM", 3), (10, "QO", 6), (11, "QC", 7)):
+        payload, polys[name] = p4([g[pos] for g in gates] + [0] * (n - ng))
+        secs.append((sid, payload))
+    sigma = [0] * (3 * n)
+    last: Dict[int, int] = {}
+    first: Dict[int, int] = {}
+    w = 1
+    for i in range(n):
+        for col in range(3):
+            p = col * n + i
+            v = w if col == 0 else (w * k1 % r if col == 1 else w * k2 % r)
+            if i >= n - 2:                      # the two blinding rows map to themselves (fflonk_setup.js:356-360)
+                sigma[p] = v
+                continue
+            s = gates[i][col] if i < ng else 0
+            if s not in last:
+                first[s] = p
+            else:
+                sigma[p] = last[s]
+            last[s] = v
+        w = w * wn % r
+    for s, p in first.items():
+        sigma[p] = last[s]
+    for col, name in enumerate(("S1", "S2", "S3")):
+        payload, polys[name] = p4(sigma[col * n:(col + 1) * n])
+        secs.append((12 + col, payload))
+    payload = b""
+    for i in range(max(n_public, 1)):
+        payload += p4([1 if j == i else 0 for j in range(n)])[0]
+    secs.append((15, payload))
+    npts = 9 * n + 18
+    pts = _tau_powers(ci, tau, npts) if structured else bytes(orc.gen_points(ci.id, 1, tau & 0xFFFFFFFF, npts))
+    secs.append((16, pts))
+    C0 = _cpoly([polys[k] for k in ("QL", "QR", "QO", "QM", "QC", "S1", "S2", "S3")])    # writeC0 :441-464
+    C0 = (C0 + [0] * (8 * n))[:8 * n]
+    secs.append((17, _mont_from_ints(ci, C0)))
+    c0_point = _commit(ci, pts, C0)
+    hdr = struct.pack("<I", ci.n8q) + ci.q.to_bytes(ci.n8q, "little") + struct.pack("<I", 32) + r.to_bytes(32, "little")
+    hdr += struct.pack("<IIIII", n_vars, n_public, n, len(additions), ng)
+    for v in (k1, k2, w3, w4, w8, wr):
+        hdr += ci.fr_to_mont(v)
+    hdr += _g2_times_gen(ci, tau) if structured else ci.g2_affine_bytes(ci.g2)
+    hdr += ci.g1_affine_bytes(c0_point)
+    return orc.write_binfile("zkey", 1, [(1, struct.pack("<I", 10)), (2, hdr)] + secs)

@@ -56,6 +56,20 @@ def test_host_fflonk_reference_fixture(hostlib, golden):
     assert fflonk.fflonk_verify(json.loads(bytes(g["vk_json"])), public, got)
 
 
+@pytest.mark.parametrize("n_gates,n_pub,with_additions", [(13, 1, True), (120, 1, True), (29, 3, True), (60, 5, False), (500, 1, True)])
+def test_host_fflonk_synthetic(hostlib, n_gates, n_pub, with_additions):
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(n_gates, n_pub=n_pub, with_additions=with_additions)
+    zkey = fflonk.fflonk_setup_synth(gates, adds, n_vars, n_pub, tau=0xFACE0FF + n_gates, structured=n_gates < 200)
+    wtns = plonk.wtns_bytes(wit)
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = fflonk.fflonk_prove(zkey, wtns, BLINDERS)
+    got = proof_from_bytes(raw)
+    assert got == want
+    if n_gates < 200:
+        assert fflonk.fflonk_verify(fflonk.fflonk_vk(zkey), public, got)
+
+
 def test_host_fflonk_errors(hostlib, golden):
     g = golden("fflonk_case.npz")
     zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])

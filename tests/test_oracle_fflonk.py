@@ -49,3 +49,14 @@ def test_wrong_witness_is_rejected(ref_case):
     from oracle.plonk import wtns_bytes
     with pytest.raises(ValueError):
         fflonk.fflonk_prove(ref_case["zkey"], wtns_bytes(wit), BLINDERS)
+
+
+@pytest.mark.parametrize("n_gates,n_pub", [(13, 1), (120, 3)])
+def test_synthetic_setup_prove_verify(n_gates, n_pub):
+    from oracle import plonk
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(n_gates, n_pub=n_pub)
+    zkey = fflonk.fflonk_setup_synth(gates, adds, n_vars, n_pub, tau=0xC0FFEE12345)
+    proof, public = fflonk.fflonk_prove(zkey, plonk.wtns_bytes(wit), BLINDERS)
+    vk = fflonk.fflonk_vk(zkey)
+    assert len(public) == n_pub and fflonk.fflonk_verify(vk, public, proof)
+    assert not fflonk.fflonk_verify(vk, [str(int(public[0]) ^ 1)] + public[1:], proof)
