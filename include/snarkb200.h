@@ -114,6 +114,19 @@ uint32_t sb_plonk_proof_bytes(sb_ctx* ctx);
 int sb_plonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,
                    uint8_t* proof_out);
 int sb_plonk_release(sb_ctx* ctx, uint64_t handle);
+/* ---- fflonk (src/fflonk_prove.js:51-1286), BN254 only like the reference's setup constants ----------------------
+ * sb_fflonk_load: an fflonk zkey (protocol id 10, sections 2-17: src/zkey_utils.js:301-339, src/fflonk_constants.js).
+ * sb_fflonk_prove: witness as for sb_plonk_prove; blinders = b_1..b_9 as 9 Montgomery field elements (:321-324);
+ *   proof_out = C1 C2 W1 W2 (affine Montgomery) then the 16 evaluations ql qr qm qo qc s1 s2 s3 a b c z zw t1w t2w inv
+ *   (Montgomery, 32 bytes each): sb_fflonk_proof_bytes().  Errors: "zkey file is not fflonk" (:71-73), "Invalid witness
+ *   length. Circuit: N, witness: M, A" (:79-81), "Copy constraints does not match" (:649-651), "Polynomial is not
+ *   divisible", "T0/T1/T2 Polynomial is not well calculated". */
+int sb_fflonk_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handle);
+int sb_fflonk_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions);
+uint32_t sb_fflonk_proof_bytes(sb_ctx* ctx);
+int sb_fflonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,
+                    uint8_t* proof_out);
+int sb_fflonk_release(sb_ctx* ctx, uint64_t handle);
 /* multi-GPU: this rank proves with its shard [shard, n_shards) of every MSM and returns the five un-normalised
  * MSM partials (A, B1, C, H in G1; B2 in G2) instead of a proof; the ranks exchange them (NCCL all-gather) and any
  * rank finishes with sb_groth16_finish. */

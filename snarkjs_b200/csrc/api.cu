@@ -65,7 +65,8 @@ struct Groth16Key {
 
 }  // namespace
 
-namespace { struct PlonkKeyDev; void plonk_free_key(PlonkKeyDev*); }   // api_plonk.inl
+namespace { struct PlonkKeyDev; void plonk_free_key(PlonkKeyDev*); }     // api_plonk.inl
+namespace { struct FflonkKeyDev; void fflonk_free_key(FflonkKeyDev*); }  // api_fflonk.inl
 
 static constexpr size_t STAGE_BYTES = 8u << 20;
 
@@ -92,6 +93,7 @@ struct sb_ctx {
     std::vector<BaseSet> bases;
     std::vector<Groth16Key*> keys;
     std::vector<PlonkKeyDev*> plonk_keys;
+    std::vector<FflonkKeyDev*> fflonk_keys;
     cudaEvent_t ev[8];
     float last_ms[8] = {0};
     int fr_s = 0, fr_bits = 254;
@@ -490,6 +492,7 @@ void sb_destroy(sb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto* k : c->keys) if (k) free_key(k);
     for (auto* k : c->plonk_keys) if (k) plonk_free_key(k);
+    for (auto* k : c->fflonk_keys) if (k) fflonk_free_key(k);
     for (auto& b : c->bases) { if (b.d) cudaFree(b.d); if (b.table) cudaFree(b.table); }
     for (auto* t : c->pre_cache) { t->lo.release(); t->hi.release(); delete t; }
     for (auto& kv : c->ntt_fwd) { kv.second.lo.release(); kv.second.hi.release(); }
@@ -1205,6 +1208,7 @@ int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen
 // ================================================================================================================
 // PLONK (src/plonk_prove.js) — templates live outside the extern "C" block
 #include "api_plonk.inl"
+#include "api_fflonk.inl"
 
 extern "C" {
 
@@ -1231,6 +1235,33 @@ int sb_plonk_release(sb_ctx* c, uint64_t h) {
     PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
     plonk_free_key(k); c->plonk_keys[h - 1] = nullptr;
+    return 0;
+}
+
+// ---- fflonk (src/fflonk_prove.js)
+int sb_fflonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle) {
+    if (!c || !zkey || !handle) return SB_ERR_ARG;
+    if (c->curve != SB_BN254) return fail(c, SB_ERR_ARG, "fflonk is defined on bn128 only (src/fflonk_setup.js:534-557)");
+    cudaSetDevice(c->device);
+    return fflonk_load_impl<BnFr>(c, zkey, len, handle);
+}
+static FflonkKeyDev* get_fflonk_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->fflonk_keys.size()) ? c->fflonk_keys[h - 1] : nullptr; }
+int sb_fflonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) {
+    FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
+    if (n_vars) *n_vars = k->z.nVars; if (n_public) *n_public = k->z.nPublic; if (domain_size) *domain_size = k->z.n; if (n_additions) *n_additions = k->z.nAdditions;
+    return 0;
+}
+uint32_t sb_fflonk_proof_bytes(sb_ctx* c) { return c ? 4 * c->g1.aff_bytes + 16 * 32 : 0; }
+int sb_fflonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders, uint8_t* proof) {
+    FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
+    if (!witness || !blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
+    cudaSetDevice(c->device);
+    return fflonk_prove_impl<BnFq, BnFr>(c, k, witness, n_witness, blinders, proof);
+}
+int sb_fflonk_release(sb_ctx* c, uint64_t h) {
+    FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
+    cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
+    fflonk_free_key(k); c->fflonk_keys[h - 1] = nullptr;
     return 0;
 }
 

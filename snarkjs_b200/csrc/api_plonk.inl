@@ -25,6 +25,7 @@ struct PlonkKeyDev {
     void* work[27] = {nullptr};              // W | 8 x n | 10 x (n + 8) | 8 x 4n   (order of PlonkWork)
     void* d_cub = nullptr; size_t cub_bytes = 0;
     int* d_flag = nullptr; void* d_red = nullptr;
+    void* commit_scratch() const { return work[18]; }   // PlonkWork::scal: free whenever a Montgomery polynomial is committed
 };
 
 void plonk_free_key(PlonkKeyDev* k) {
@@ -33,8 +34,10 @@ void plonk_free_key(PlonkKeyDev* k) {
     delete k;
 }
 
-template <class F> struct CudaPlonkBackend {
-    sb_ctx* c; PlonkKeyDev* key; int rc = 0;
+// K = the device-side key (PlonkKeyDev here, FflonkKeyDev in api_fflonk.inl): both expose d_flag, d_red, d_cub, cub_bytes,
+// d_ptau, t_ptau, gp, d_pow, pow_h, pow_nhi and commit_scratch()
+template <class F, class K = PlonkKeyDev> struct CudaPlonkBackend {
+    sb_ctx* c; K* key; int rc = 0;
     cudaStream_t st() const { return c->stream; }
     void note(cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) rc = cuda_fail(c, e, what); }
     void launched(const char* what) { c->launches++; note(cudaGetLastError(), what); }
@@ -68,7 +71,7 @@ template <class F> struct CudaPlonkBackend {
     }
     int commit(const F* coef, uint64_t len, uint8_t* affine) {
         if (rc) return rc;
-        F* scal = (F*)key->work[18];                 // PlonkWork::scal: free whenever a Montgomery polynomial is committed
+        F* scal = (F*)key->commit_scratch();
         int r = fr_convert(c->curve, coef, scal, len, 0, st()); c->launches++;
         if (r) return cuda_fail(c, (cudaError_t)r, "fr_convert");
         return commit_plain(scal, len, affine);
