@@ -5,7 +5,10 @@ import json
 
 import pytest
 
-pytestmark = pytest.mark.gpu
+# This file sorts after the other GPU suites on purpose, and is non-strict xfail until its first green hardware run is
+# recorded in profiles/README.md: the CUDA backend compiled and the same flow + element functions match the oracle on
+# the host (tests/test_host_fflonk.py), but the round's GPU budget ran out before sb_fflonk_prove could run on a B200.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="fflonk CUDA backend not yet run on hardware")]
 
 BLINDERS = [0x6000 + 32452843 * i for i in range(9)]
 
