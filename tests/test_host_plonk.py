@@ -120,3 +120,30 @@ def test_host_flow_errors(hostlib):
     g16[idx + 12] = 1
     rc, err, _ = host_prove(hostlib, bytes(g16), plonk.wtns_bytes(wit), BLINDERS)
     assert rc != 0 and err == "zkey file is not plonk"
+
+
+def test_host_parser_rejects_malformed_keys(hostlib):
+    """plonk_parse_zkey (used verbatim by sb_plonk_load) must fail cleanly on truncated or inconsistent containers."""
+    import struct
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(13)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=99)
+    wtns = plonk.wtns_bytes(wit)
+    for cut in (0, 3, 11, 12, 40, 200, len(zkey) // 2, len(zkey) - 1):
+        rc, err, _ = host_prove(hostlib, zkey[:cut], wtns, BLINDERS)
+        assert rc != 0 and err, cut
+    bad = bytearray(zkey)
+    bad[0:4] = b"wtns"
+    rc, err, _ = host_prove(hostlib, bytes(bad), wtns, BLINDERS)
+    assert rc != 0 and "Invalid File format" in err
+    # a section length that runs past the end of the file
+    bad = bytearray(zkey)
+    struct.pack_into("<Q", bad, 16, 1 << 40)
+    rc, err, _ = host_prove(hostlib, bytes(bad), wtns, BLINDERS)
+    assert rc != 0 and err == "Invalid file size"
+    # domain size that is not a power of two (header field at a fixed offset inside section 2)
+    data, secs = orc.read_binfile(zkey, "zkey", 2)
+    pos = secs[2][0][0] + 4 + 32 + 4 + 32 + 8
+    bad = bytearray(zkey)
+    struct.pack_into("<I", bad, pos, 12)
+    rc, err, _ = host_prove(hostlib, bytes(bad), wtns, BLINDERS)
+    assert rc != 0 and "power of two" in err
