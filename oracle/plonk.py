@@ -21,6 +21,10 @@ Pins (tests/test_oracle_plonk.py), and what is NOT pinned:
     from plonk_setup_synth.  Prover and verifier restate two different reference files (plonk_prove.js /
     plonk_verify.js), so algebra slips show up as a failed verification.
   * the NTT / MSM primitives underneath are pinned byte-for-byte by the zkey sections (tests/test_oracle_golden.py).
+  * the transcript's byte layout (32-byte big-endian words: Qm.x, Qm.y, ..., S3.y, the public signals, A, B, C; then
+    beta -> gamma; beta, gamma, Z -> alpha; alpha, T1..T3 -> xi; xi, 6 evaluations -> v; Wxi, Wxiw -> u; keccak256
+    reduced mod r) is stated a third time, independently, by the reference's current Solidity template
+    templates/verifier_plonk.sol.ejs:256-360, and agrees with Transcript / _challenges below.
   * NOT pinned: the prover's bytes (the reference draws the blinders b1..b11 with Fr.random(), plonk_prove.js:246-249;
     here they are inputs) and the transcript's byte layout beyond what prover and verifier share.  The stored
     test/plonk_circuit/proof.json cannot serve: it is a stale development artifact — it is rejected by this restatement
