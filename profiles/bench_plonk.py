@@ -8,6 +8,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("OMP_NUM_THREADS", "8")   # the CPU-side key setup is many small oracle calls: wide OpenMP teams only add latency
 T0 = time.time()
 import numpy as np                      # noqa: E402
 import snarkjs_b200                     # noqa: E402
