@@ -5,10 +5,11 @@ import json
 
 import pytest
 
-# This file sorts after the other GPU suites on purpose, and is non-strict xfail until its first green hardware run is
-# recorded in profiles/README.md: the CUDA backend compiled and the same flow + element functions match the oracle on
-# the host (tests/test_host_fflonk.py), but the round's GPU budget ran out before sb_fflonk_prove could run on a B200.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="fflonk CUDA backend not yet run on hardware")]
+# This file sorts after the other GPU suites on purpose.  First hardware run (profiles/fflonk_first_gpu_run_r1.log, the
+# round's last 81 s of GPU budget): the reference fixture and the first three synthetic keys passed before the time limit
+# cut the run; the cases that had not finished are non-strict xfail until they have a recorded green run.
+pytestmark = pytest.mark.gpu
+NOT_YET_RUN = pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (round-1 GPU budget exhausted)")
 
 BLINDERS = [0x6000 + 32452843 * i for i in range(9)]
 
@@ -42,7 +43,8 @@ def test_fflonk_reference_fixture(env, golden):
         pk.release()
 
 
-@pytest.mark.parametrize("n_gates,n_pub,with_additions", [(13, 1, True), (120, 3, True), (500, 1, False), (2000, 1, True)])
+@pytest.mark.parametrize("n_gates,n_pub,with_additions", [(13, 1, True), (120, 3, True), (500, 1, False),
+                                                          pytest.param(2000, 1, True, marks=NOT_YET_RUN)])
 def test_fflonk_synthetic(env, n_gates, n_pub, with_additions):
     """2000 gates -> domain 2048, 18450 PTau points: the MSMs run in table mode."""
     op, off = env["op"], env["off"]
@@ -61,6 +63,7 @@ def test_fflonk_synthetic(env, n_gates, n_pub, with_additions):
         pk.release()
 
 
+@NOT_YET_RUN
 def test_fflonk_errors(env, golden):
     sb, op, off, orc = env["sb"], env["op"], env["off"], env["orc"]
     g = golden("fflonk_case.npz")
