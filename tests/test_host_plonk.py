@@ -147,3 +147,20 @@ def test_host_parser_rejects_malformed_keys(hostlib):
     struct.pack_into("<I", bad, pos, 12)
     rc, err, _ = host_prove(hostlib, bytes(bad), wtns, BLINDERS)
     assert rc != 0 and "power of two" in err
+
+
+def test_host_flow_with_emulated_ptx_arithmetic(tmp_path, golden):
+    """Same flow with fp.cuh's device code path (PTX carry chains emulated instruction by instruction) instead of the
+    fast host multiply: the arithmetic the kernels execute, inside the PLONK element functions."""
+    so = str(tmp_path / "libhostplonk_ptx.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DSB_HOST_EMULATE_PTX", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "host", "host_plonk.cpp"), "-ldl"])
+    lib = ctypes.CDLL(so)
+    lib.hp_plonk_prove.restype = ctypes.c_int
+    lib.hp_plonk_prove.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64,
+                                   ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    g = golden("plonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    rc, err, raw = host_prove(lib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    assert proof_from_bytes(raw) == plonk.plonk_prove(zkey, wtns, BLINDERS)[0]
