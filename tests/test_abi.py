@@ -47,7 +47,7 @@ def test_product_does_not_import_oracle():
         if "build" in dirpath:
             continue
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inl")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt and "snark_oracle" not in txt, f
 
@@ -64,3 +64,18 @@ def test_shard_range_partitions():
                 nxt = a.value + b.value
                 tot += b.value
             assert tot == total and nxt == total
+
+
+def test_prover_entry_points_reject_null_context():
+    """The PLONK / fflonk entry points return SB_ERR_ARG (-1) instead of touching a null context."""
+    L = N.lib()
+    h = ctypes.c_uint64()
+    buf = ctypes.create_string_buffer(64)
+    for load in (L.sb_plonk_load, L.sb_fflonk_load):
+        assert load(None, buf, 64, ctypes.byref(h)) == -1
+    for prove in (L.sb_plonk_prove, L.sb_fflonk_prove):
+        assert prove(None, 1, buf, 1, buf.raw, buf) == -1
+    for release in (L.sb_plonk_release, L.sb_fflonk_release):
+        assert release(None, 1) == -1
+    assert L.sb_plonk_proof_bytes(None) == 0 and L.sb_fflonk_proof_bytes(None) == 0
+    assert L.sb_plonk_info(None, 1, None, None, None, None) == -1 and L.sb_fflonk_info(None, 1, None, None, None, None) == -1
