@@ -109,6 +109,8 @@ int sb_groth16_release(sb_ctx* ctx, uint64_t handle);
  *   "Invalid witness length. Circuit: N, witness: M, A", "Copy constraints does not match" (:436-438),
  *   "Polynomial is not divisible" (polynomial.js:608, 653), "T Polynomial is not well calculated" (:648-650). */
 int sb_plonk_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handle);
+/* same from a file: the .zkey is mapped read-only and streamed to HBM section by section */
+int sb_plonk_load_file(sb_ctx* ctx, const char* zkey_path, uint64_t* handle);
 int sb_plonk_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions);
 uint32_t sb_plonk_proof_bytes(sb_ctx* ctx);
 int sb_plonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,
@@ -122,6 +124,7 @@ int sb_plonk_release(sb_ctx* ctx, uint64_t handle);
  *   length. Circuit: N, witness: M, A" (:79-81), "Copy constraints does not match" (:649-651), "Polynomial is not
  *   divisible", "T0/T1/T2 Polynomial is not well calculated". */
 int sb_fflonk_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handle);
+int sb_fflonk_load_file(sb_ctx* ctx, const char* zkey_path, uint64_t* handle);
 int sb_fflonk_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions);
 uint32_t sb_fflonk_proof_bytes(sb_ctx* ctx);
 int sb_fflonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,

@@ -47,11 +47,13 @@ _SIGNATURES = {
     "sb_groth16_prove_wtns": (ctypes.c_int, [vp, u64, vp, u64, vp, vp, vp]),
     "sb_groth16_release": (ctypes.c_int, [vp, u64]),
     "sb_plonk_load": (ctypes.c_int, [vp, vp, u64, ctypes.POINTER(u64)]),
+    "sb_plonk_load_file": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.POINTER(u64)]),
     "sb_plonk_info": (ctypes.c_int, [vp, u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "sb_plonk_proof_bytes": (u32, [vp]),
     "sb_plonk_prove": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_char_p, vp]),
     "sb_plonk_release": (ctypes.c_int, [vp, u64]),
     "sb_fflonk_load": (ctypes.c_int, [vp, vp, u64, ctypes.POINTER(u64)]),
+    "sb_fflonk_load_file": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.POINTER(u64)]),
     "sb_fflonk_info": (ctypes.c_int, [vp, u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "sb_fflonk_proof_bytes": (u32, [vp]),
     "sb_fflonk_prove": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_char_p, vp]),

@@ -9,6 +9,10 @@
 #include <map>
 #include <algorithm>
 #include <mutex>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include "../../include/snarkb200.h"
 #include "ec.cuh"
 #include "msm.cuh"
@@ -1217,6 +1221,23 @@ int sb_plonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle
     cudaSetDevice(c->device);
     return c->curve == SB_BN254 ? plonk_load_impl<BnFr>(c, zkey, len, handle) : plonk_load_impl<BlsFr>(c, zkey, len, handle);
 }
+// maps the file read-only and hands it to the byte loader: the sections are read once, front to back, through the pinned
+// staging buffers (h2d), so the key never sits in anonymous host memory
+static int load_mapped(sb_ctx* c, const char* path, uint64_t* handle, int (*load)(sb_ctx*, const uint8_t*, uint64_t, uint64_t*)) {
+    if (!c || !path || !handle) return SB_ERR_ARG;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(c, SB_ERR_FORMAT, std::string("cannot open ") + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); return fail(c, SB_ERR_FORMAT, std::string("cannot stat ") + path); }
+    void* p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(c, SB_ERR_FORMAT, std::string("cannot map ") + path);
+    madvise(p, (size_t)st.st_size, MADV_SEQUENTIAL);
+    int rc = load(c, (const uint8_t*)p, (uint64_t)st.st_size, handle);
+    munmap(p, (size_t)st.st_size);
+    return rc;
+}
+int sb_plonk_load_file(sb_ctx* c, const char* path, uint64_t* handle) { return load_mapped(c, path, handle, sb_plonk_load); }
 static PlonkKeyDev* get_plonk_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->plonk_keys.size()) ? c->plonk_keys[h - 1] : nullptr; }
 int sb_plonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) {
     PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
@@ -1245,6 +1266,7 @@ int sb_fflonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handl
     cudaSetDevice(c->device);
     return fflonk_load_impl<BnFr>(c, zkey, len, handle);
 }
+int sb_fflonk_load_file(sb_ctx* c, const char* path, uint64_t* handle) { return load_mapped(c, path, handle, sb_fflonk_load); }
 static FflonkKeyDev* get_fflonk_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->fflonk_keys.size()) ? c->fflonk_keys[h - 1] : nullptr; }
 int sb_fflonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) {
     FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");

@@ -64,6 +64,21 @@ class ProvingKey:
         for k in ("nVars", "nPublic", "domainSize", "nAdditions"):
             setattr(self, k, self.header[k])
 
+    @classmethod
+    def from_file(cls, path: str, curve: Curve):
+        """Loads the key from disk (sb_plonk_load_file: mapped read-only, streamed to HBM section by section)."""
+        self = cls.__new__(cls)
+        self.curve, self._own_curve = curve, False
+        h = ctypes.c_uint64()
+        curve.check(curve.lib.sb_plonk_load_file(curve.handle, path.encode(), ctypes.byref(h)))   # validates the container
+        self.handle = h.value
+        nv, npub, ds, na = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        curve.check(curve.lib.sb_plonk_info(curve.handle, self.handle, ctypes.byref(nv), ctypes.byref(npub), ctypes.byref(ds), ctypes.byref(na)))
+        self.nVars, self.nPublic, self.domainSize, self.nAdditions = nv.value, npub.value, ds.value, na.value
+        self.header = {"protocol": "plonk", "r": curve.r, "q": curve.q, "nVars": nv.value, "nPublic": npub.value, "domainSize": ds.value,
+                       "nAdditions": na.value, "power": ds.value.bit_length() - 1}
+        return self
+
     def prove_raw(self, witness, blinders: bytes) -> bytes:
         """witness = wtns section 2 ((nVars - nAdditions) x 32 bytes, plain LE); blinders = 11 x 32 Montgomery bytes."""
         w = _arr(witness)

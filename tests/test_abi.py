@@ -73,6 +73,8 @@ def test_prover_entry_points_reject_null_context():
     buf = ctypes.create_string_buffer(64)
     for load in (L.sb_plonk_load, L.sb_fflonk_load):
         assert load(None, buf, 64, ctypes.byref(h)) == -1
+    for load_file in (L.sb_plonk_load_file, L.sb_fflonk_load_file):
+        assert load_file(None, b"/nonexistent.zkey", ctypes.byref(h)) == -1
     for prove in (L.sb_plonk_prove, L.sb_fflonk_prove):
         assert prove(None, 1, buf, 1, buf.raw, buf) == -1
     for release in (L.sb_plonk_release, L.sb_fflonk_release):

@@ -96,6 +96,25 @@ def test_plonk_bls12381(env):
         curve.terminate()
 
 
+@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
+def test_plonk_key_from_file(env, golden, tmp_path):
+    """sb_plonk_load_file: the key mapped from disk gives the same proof as the key loaded from bytes."""
+    g = golden("plonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    path = tmp_path / "circuit.zkey"
+    path.write_bytes(zkey)
+    pk = env["sb"].plonk.ProvingKey.from_file(str(path), env["curve"])
+    try:
+        ref = env["op"].read_plonk_zkey(zkey)
+        assert (pk.nVars, pk.nPublic, pk.domainSize, pk.nAdditions) == (ref["nVars"], ref["nPublic"], ref["domainSize"], ref["nAdditions"])
+        proof, public = env["sb"].plonk.prove(pk, wtns, env["bl"])
+        assert (proof, public) == env["op"].plonk_prove(zkey, wtns, BLINDERS)
+    finally:
+        pk.release()
+    with pytest.raises(env["sb"].SbError, match="cannot open"):
+        env["sb"].plonk.ProvingKey.from_file(str(tmp_path / "missing.zkey"), env["curve"])
+
+
 def test_plonk_errors(env, golden):
     sb, op, orc = env["sb"], env["op"], env["orc"]
     gates, adds, n_vars, n_pub, wit = op.chain_gates(60)

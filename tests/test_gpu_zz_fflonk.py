@@ -64,6 +64,19 @@ def test_fflonk_synthetic(env, n_gates, n_pub, with_additions):
 
 
 @NOT_YET_RUN
+def test_fflonk_key_from_file(env, golden, tmp_path):
+    g = golden("fflonk_case.npz")
+    zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
+    path = tmp_path / "circuit.zkey"
+    path.write_bytes(zkey)
+    pk = env["sb"].fflonk.ProvingKey.from_file(str(path), env["curve"])
+    try:
+        assert (env["sb"].fflonk.prove(pk, wtns, env["bl"])) == env["off"].fflonk_prove(zkey, wtns, BLINDERS)
+    finally:
+        pk.release()
+
+
+@NOT_YET_RUN
 def test_fflonk_errors(env, golden):
     sb, op, off, orc = env["sb"], env["op"], env["off"], env["orc"]
     g = golden("fflonk_case.npz")
