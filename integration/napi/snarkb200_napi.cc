@@ -103,6 +103,22 @@ Napi::Value Groth16Prove(const Napi::CallbackInfo& info) {
   return Queue(info.Env(), c, 8 * n8q, [=](std::vector<uint8_t>& out) { return sb_groth16_prove(c, h, pw, nw, pr, ps, out.data()); }, {w, r, s});
 }
 
+// plonkLoad / fflonkLoad(ctx, zkeyBytes) -> handle ; plonkProve / fflonkProve(ctx, handle, witnessSection, blinders) -> Promise<Buffer>
+// (src/plonk_prove.js:47, src/fflonk_prove.js:51; blinders = 11 resp. 9 Fr.random() elements concatenated)
+template <int (*LOAD)(sb_ctx*, const uint8_t*, uint64_t, uint64_t*)>
+Napi::Value KeyLoad(const Napi::CallbackInfo& info) {
+  sb_ctx* c = ctx_of(info[0]); auto z = info[1].As<Napi::Uint8Array>(); uint64_t h = 0;
+  if (LOAD(c, z.Data(), z.ByteLength(), &h)) { Napi::Error::New(info.Env(), sb_last_error(c)).ThrowAsJavaScriptException(); return info.Env().Undefined(); }
+  return Napi::Number::New(info.Env(), (double)h);
+}
+template <int (*PROVE)(sb_ctx*, uint64_t, const uint8_t*, uint64_t, const uint8_t*, uint8_t*), uint32_t (*BYTES)(sb_ctx*)>
+Napi::Value KeyProve(const Napi::CallbackInfo& info) {
+  sb_ctx* c = ctx_of(info[0]); uint64_t h = (uint64_t)info[1].As<Napi::Number>().Int64Value();
+  auto w = info[2].As<Napi::Uint8Array>(); auto b = info[3].As<Napi::Uint8Array>();
+  size_t nw = w.ByteLength() / 32; const uint8_t *pw = w.Data(), *pb = b.Data();
+  return Queue(info.Env(), c, BYTES(c), [=](std::vector<uint8_t>& out) { return PROVE(c, h, pw, nw, pb, out.data()); }, {w, b});
+}
+
 Napi::Object Init(Napi::Env env, Napi::Object exports) {
   exports.Set("createContext", Napi::Function::New(env, Create));
   exports.Set("multiExpAffine", Napi::Function::New(env, MultiExpAffine));
@@ -112,6 +128,10 @@ Napi::Object Init(Napi::Env env, Napi::Object exports) {
   exports.Set("qapJoinAbc", Napi::Function::New(env, QapJoinAbc));
   exports.Set("groth16Load", Napi::Function::New(env, Groth16Load));
   exports.Set("groth16Prove", Napi::Function::New(env, Groth16Prove));
+  exports.Set("plonkLoad", Napi::Function::New(env, KeyLoad<sb_plonk_load>));
+  exports.Set("plonkProve", Napi::Function::New(env, KeyProve<sb_plonk_prove, sb_plonk_proof_bytes>));
+  exports.Set("fflonkLoad", Napi::Function::New(env, KeyLoad<sb_fflonk_load>));
+  exports.Set("fflonkProve", Napi::Function::New(env, KeyProve<sb_fflonk_prove, sb_fflonk_proof_bytes>));
   return exports;
 }
 
