@@ -598,11 +598,13 @@ def plonk_prove(zkey, wtns, blinders: Sequence[int], return_parts: bool = False)
 
 
 # ----------------------------------------------------------------------------- synthetic structured setup
-def chain_gates(n_gates: int, seed: int = 7, r: int = orc.P_BN_R, n_pub: int = 1, with_additions: bool = True):
+def chain_gates(n_gates: int, seed: int = 7, r: int = orc.P_BN_R, n_pub: int = 1, with_additions: bool = True,
+                deep_additions: bool = False):
     """A PLONK circuit given directly as gates (the reference derives them from an r1cs, plonk_setup.js:142-299):
     the chain x_{i+1} = x_i^2 + c with public output x_m (and, for n_pub > 1, x_0, x_1, ... as further public signals),
     plus linear 'addition' wires y_j = 3 x_j + 7 x_{j+1} and z_j = y_j + 2 y_{j+1} (the shape reduceCoefs emits,
-    plonk_setup.js:176-215), so calculateAdditions is exercised with two dependency levels.
+    plonk_setup.js:176-215), so calculateAdditions is exercised with two dependency levels; deep_additions=True makes
+    y_j = 3 x_j + 7 y_{j-1} instead, a dependency chain as long as the number of additions.
     Returns (gates, additions, n_vars, n_public, witness ints for the wtns file).
     gate = (sl, sr, so, qm, ql, qr, qo, qc) with plain ints; the first n_pub gates are the public-input gates
     (plonk_setup.js:285-297)."""
@@ -625,8 +627,9 @@ def chain_gates(n_gates: int, seed: int = 7, r: int = orc.P_BN_R, n_pub: int = 1
     wire_y = []
     for j in range(n_y):
         so = n_wit + len(additions)
-        additions.append((wire_x[j], wire_x[j + 1], 3, 7))
-        gates.append((wire_x[j], wire_x[j + 1], so, 0, (-3) % r, (-7) % r, 1, 0))
+        other = wire_y[j - 1] if (deep_additions and j) else wire_x[j + 1]
+        additions.append((wire_x[j], other, 3, 7))
+        gates.append((wire_x[j], other, so, 0, (-3) % r, (-7) % r, 1, 0))
         wire_y.append(so)
     for j in range(n_z):
         so = n_wit + len(additions)

@@ -78,6 +78,20 @@ def test_plonk_shapes(env, n_gates, n_pub, with_additions):
         pk.release()
 
 
+@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
+def test_plonk_deep_addition_chain(env):
+    """Every addition depends on the previous one: one k_pl_additions launch per addition (dependency levels)."""
+    op = env["op"]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(100, deep_additions=True)
+    zkey = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=424242)
+    wtns = op.wtns_bytes(wit)
+    pk = env["sb"].plonk.ProvingKey(zkey, env["curve"])
+    try:
+        assert env["sb"].plonk.prove(pk, wtns, env["bl"]) == op.plonk_prove(zkey, wtns, BLINDERS)
+    finally:
+        pk.release()
+
+
 def test_plonk_bls12381(env):
     """BLS12-381: 12-limb base field (transcript, MSM), its own Fr roots; parity with the oracle (no pairing check)."""
     sb, op, orc = env["sb"], env["op"], env["orc"]

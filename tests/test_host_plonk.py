@@ -93,6 +93,19 @@ def test_host_flow_shapes(hostlib, n_gates, n_pub, with_additions):
     assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, got)
 
 
+def test_host_flow_deep_addition_chain(hostlib):
+    """Additions that each depend on the previous one: one dependency level per addition (plonk_addition_levels must keep
+    the reference's sequential semantics, plonk_prove.js:166-211)."""
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(100, deep_additions=True)
+    assert len(adds) > 20
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=424242)
+    wtns = plonk.wtns_bytes(wit)
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    assert proof_from_bytes(raw) == want and plonk.plonk_verify(plonk.plonk_vk(zkey), public, want)
+
+
 def test_host_flow_bls12381(hostlib):
     """Same flow on BLS12-381 (12-limb base field in the transcript, 255-bit scalar field); no pairing check here."""
     ci = orc.CURVES[orc.BLS12_381]
