@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 domain of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--witness-like", action="store_true", help="witness distribution of real circuits (SURVEY 8d): 50% zeros, 25% ones, 25% uniform")
+    ap.add_argument("--witness-like", action="store_true", help="witness distribution of real circuits (SURVEY 8d): 50%% zeros, 25%% ones, 25%% uniform")
     ap.add_argument("--check-oracle", action="store_true", help="also prove the full workload with the CPU oracle and compare proof bytes (minutes)")
     return ap.parse_args()
 
