@@ -543,9 +543,9 @@ def fflonk_setup_synth(gates, additions, n_vars: int, n_public: int, tau: int, s
         secs.append((4 + pos, np.array([g[pos] for g in gates], dtype="<u4").tobytes()))
 
     def p4(evals):
-        coef = _ifft(ci, evals)
-        ev4 = orc.fr_fft(ci.id, _mont_from_ints(ci, coef + [0] * (3 * n)), False)
-        return _mont_from_ints(ci, coef) + bytes(ev4), coef
+        coef = bytes(orc.fr_fft(ci.id, _mont_from_ints(ci, evals), True))          # Montgomery bytes throughout
+        ev4 = orc.fr_fft(ci.id, coef + bytes(3 * n * 32), False)
+        return coef + bytes(ev4), coef
 
     polys = {}
     # gate tuple = (sl, sr, so, qm, ql, qr, qo, qc); sections 7..11 hold QL QR QM QO QC
@@ -582,10 +582,15 @@ def fflonk_setup_synth(gates, additions, n_vars: int, n_public: int, tau: int, s
     npts = 9 * n + 18
     pts = _tau_powers(ci, tau, npts) if structured else bytes(orc.gen_points(ci.id, 1, tau & 0xFFFFFFFF, npts))
     secs.append((16, pts))
-    C0 = _cpoly([polys[k] for k in ("QL", "QR", "QO", "QM", "QC", "S1", "S2", "S3")])    # writeC0 :441-464
-    C0 = (C0 + [0] * (8 * n))[:8 * n]
-    secs.append((17, _mont_from_ints(ci, C0)))
-    c0_point = _commit(ci, pts, C0)
+    # writeC0 :441-464: C0[8 i + j] = P_j[i] (all eight have n coefficients, so interleaving the byte rows is the CPolynomial)
+    rows = np.stack([np.frombuffer(polys[k], dtype=np.uint8).reshape(n, 32) for k in ("QL", "QR", "QO", "QM", "QC", "S1", "S2", "S3")], axis=1)
+    c0_bytes = rows.reshape(8 * n * 32).tobytes()
+    secs.append((17, c0_bytes))
+    if structured:
+        jac = orc.multiexp_affine(ci.id, 1, pts[:8 * n * 2 * ci.n8q], bytes(orc.batch_convert(ci.fr, False, c0_bytes)))
+        c0_point = ci.g1_from_affine_bytes(orc.g_to_affine(ci.id, 1, jac)[:2 * ci.n8q])
+    else:
+        c0_point = ci.g1_from_affine_bytes(pts[:2 * ci.n8q])       # any valid point: the transcript only hashes it
     hdr = struct.pack("<I", ci.n8q) + ci.q.to_bytes(ci.n8q, "little") + struct.pack("<I", 32) + r.to_bytes(32, "little")
     hdr += struct.pack("<IIIII", n_vars, n_public, n, len(additions), ng)
     for v in (k1, k2, w3, w4, w8, wr):

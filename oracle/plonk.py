@@ -661,18 +661,24 @@ def plonk_setup_synth(gates, additions, n_vars: int, n_public: int, tau: int, st
     for pos in range(3):
         secs.append((4 + pos, np.array([g[pos] for g in gates], dtype="<u4").tobytes()))
 
-    def p4(evals: List[int]) -> Tuple[bytes, List[int]]:                           # writeP4, plonk_setup.js:331-338
-        coef = _ifft(ci, evals)
-        ev4 = orc.fr_fft(ci.id, _mont_from_ints(ci, coef + [0] * (3 * n)), False)
-        return _mont_from_ints(ci, coef) + bytes(ev4), coef
+    def p4(evals: List[int]) -> Tuple[bytes, bytes]:                               # writeP4, plonk_setup.js:331-338
+        coef = bytes(orc.fr_fft(ci.id, _mont_from_ints(ci, evals), True))          # Montgomery bytes throughout
+        ev4 = orc.fr_fft(ci.id, coef + bytes(3 * n * 32), False)
+        return coef + bytes(ev4), coef
 
     if structured:
         pts = _tau_powers(ci, tau, n + 6)
     else:
         pts = bytes(orc.gen_points(ci.id, 1, tau & 0xFFFFFFFF, n + 6))
+    sG1 = 2 * ci.n8q
+    cheap = [ci.g1_from_affine_bytes(pts[i * sG1:(i + 1) * sG1]) for i in range(8)]
 
-    def commit_coef(coef):
-        return _commit(ci, pts, coef)
+    def commit_coef(coef: bytes):
+        """[q(tau)]_1 for structured keys; for unstructured ones any valid point serves (the transcript only hashes it)."""
+        if not structured:
+            return cheap.pop()
+        jac = orc.multiexp_affine(ci.id, 1, pts[:n * sG1], bytes(orc.batch_convert(ci.fr, False, coef)))
+        return ci.g1_from_affine_bytes(orc.g_to_affine(ci.id, 1, jac)[:sG1])
 
     header_pts = {}
     for pos, (sid, name) in enumerate(((7, "Qm"), (8, "Ql"), (9, "Qr"), (10, "Qo"), (11, "Qc"))):
