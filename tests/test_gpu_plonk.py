@@ -62,6 +62,7 @@ def test_plonk_synthetic(env, n_gates, structured):
         pk.release()
 
 
+@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
 @pytest.mark.parametrize("n_gates,n_pub,with_additions", [(29, 3, True), (60, 5, False)])
 def test_plonk_shapes(env, n_gates, n_pub, with_additions):
     """Several public inputs (PI(X) sums several Lagrange polynomials) and a key without additions."""
