@@ -159,7 +159,8 @@ int sb_dev_free(sb_ctx* ctx, void* p);
 int sb_dev_upload(sb_ctx* ctx, void* dst_dev, const uint8_t* src, uint64_t bytes);
 int sb_dev_download(sb_ctx* ctx, uint8_t* dst, const void* src_dev, uint64_t bytes);
 /* timing of the last call on this context, measured with CUDA events on the context's stream (ms):
- * which = 0 total device time of the call, 1.. = per-stage breakdown where the call defines one. */
+ * which = 0 total device time of the call, 1.. = per-stage breakdown where the call defines one.
+ * sb_plonk_prove / sb_fflonk_prove: 1..5 = host wall clock of rounds 1..5 (each round ends on a synchronising commit). */
 float sb_last_ms(sb_ctx* ctx, int which);
 /* counters of the last MSM / prove call: 0/1 = summed device time (ms) of the G1 / G2 bucket-accumulation kernel
  * launches, 2/3 = number of those launches, 4/5 = (scalar digit, point) entries they consumed. */

@@ -36,7 +36,7 @@ for lg in sizes:
     t_load = time.time() - t
     del zkey
     first = pk.prove_raw(W, bl)
-    ms, dev = [], []
+    ms, dev, rounds = [], [], []
     l0 = curve.launch_count()
     reps = 5 if lg <= 16 else 3
     for _ in range(reps):
@@ -44,11 +44,13 @@ for lg in sizes:
         raw = pk.prove_raw(W, bl)
         ms.append((time.perf_counter() - t) * 1e3)
         dev.append(curve.last_ms(0))
+        rounds.append([curve.last_ms(i) for i in range(1, 6)])
     launches = (curve.launch_count() - l0) // reps
     assert raw == first
     line = {"what": "plonk_prove", "curve": "bn128", "log2_domain": lg, "n_public": n_pub, "n_additions": len(adds),
             "ms_e2e_median": round(float(np.median(ms)), 3), "ms_min": round(min(ms), 3), "proofs_per_s": round(1e3 / float(np.median(ms)), 2),
             "ms_flow_device_clock": round(float(np.median(dev)), 3), "launches_per_proof": int(launches),
+            "ms_rounds_1_to_5": [round(float(x), 3) for x in np.median(np.array(rounds), axis=0)],
             "key_load_s": round(t_load, 2), "cpu_setup_s": round(t_setup, 1), "witness_bytes": int(W.size)}
     print(json.dumps(line), flush=True)
     with open("gpurun_out/plonk_bench.jsonl", "a") as f:

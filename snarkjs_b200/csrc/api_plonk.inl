@@ -7,6 +7,7 @@
 //                     (msm.cuh, table mode).  Only the transcript hashing and ~40 scalar operations run on the host.
 //
 // No CPU fallback: every bulk step is a kernel launch on c->stream.
+#include <chrono>
 #include <cub/cub.cuh>
 #include "plonk_flow.h"
 
@@ -38,6 +39,13 @@ void plonk_free_key(PlonkKeyDev* k) {
 // d_ptau, t_ptau, gp, d_pow, pow_h, pow_nhi and commit_scratch()
 template <class F, class K = PlonkKeyDev> struct CudaPlonkBackend {
     sb_ctx* c; K* key; int rc = 0;
+    std::chrono::steady_clock::time_point t_mark = std::chrono::steady_clock::now();
+    // end of round r: host wall clock since the previous mark (each round ends on a synchronising commit) -> sb_last_ms(r)
+    void mark(int r) {
+        auto now = std::chrono::steady_clock::now();
+        if (r >= 1 && r <= 5) c->last_ms[r] = std::chrono::duration<float, std::milli>(now - t_mark).count();
+        t_mark = now;
+    }
     cudaStream_t st() const { return c->stream; }
     void note(cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) rc = cuda_fail(c, e, what); }
     void launched(const char* what) { c->launches++; note(cudaGetLastError(), what); }

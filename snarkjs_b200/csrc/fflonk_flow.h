@@ -178,6 +178,7 @@ int fflonk_prove_flow(B& be, const FflonkKeyView<Fp<PR>>& k, FflonkWork<Fp<PR>>&
         be.interleave(parts, 8 * n, w.C1);
         int rc = be.commit(w.C1, 8 * n, pt_C1); if (rc) return rc;
     }
+    be.mark(1);
     // ---------------- round 2 (:522-830)
     PlonkTranscript<PQ, PR> tr;
     std::vector<F> pubA(k.nPublic);
@@ -219,6 +220,7 @@ int fflonk_prove_flow(B& be, const FflonkKeyView<Fp<PR>>& k, FflonkWork<Fp<PR>>&
         be.interleave(parts, 9 * n, w.C2);
         int rc = be.commit(w.C2, 9 * n, pt_C2); if (rc) return rc;
     }
+    be.mark(2);
     // ---------------- round 3 (:832-931)
     tr.reset(); tr.add_scalar(r.gamma); tr.add_point(pt_C2);
     const F xi_seed = tr.challenge();
@@ -246,6 +248,7 @@ int fflonk_prove_flow(B& be, const FflonkKeyView<Fp<PR>>& k, FflonkWork<Fp<PR>>&
     ev[12] = be.eval(w.cZ, n + 3, pxiw, w.G, w.P);
     ev[13] = be.eval(w.pT1, 2 * n, pxiw, w.G, w.P);
     ev[14] = be.eval(w.pT2, 4 * n, pxiw, w.G, w.P);
+    be.mark(3);
     // ---------------- round 4 (:933-1057)
     tr.reset(); tr.add_scalar(xi_seed);
     for (int j = 0; j < 15; j++) tr.add_scalar(ev[j]);
@@ -278,6 +281,7 @@ int fflonk_prove_flow(B& be, const FflonkKeyView<Fp<PR>>& k, FflonkWork<Fp<PR>>&
         be.add3(9 * n, w.Fq, w.F1, w.F2, w.Fq);
         int rc = be.commit(w.Fq, 9 * n, pt_W1); if (rc) return rc;
     }
+    be.mark(4);
     // ---------------- round 5 (:1059-1180)
     tr.reset(); tr.add_scalar(alpha); tr.add_point(pt_W1);
     const F y = tr.challenge();
@@ -301,6 +305,7 @@ int fflonk_prove_flow(B& be, const FflonkKeyView<Fp<PR>>& k, FflonkWork<Fp<PR>>&
         if (flag) { err = "Degree of L(X)/(ZTS2(y)(X-y)) remainder should be 0"; return 4; }
         int rc = be.commit_plain(w.scal, 9 * n, pt_W2); if (rc) return rc;
     }
+    be.mark(5);
     // ---------------- the batched inverse (:1182-1285)
     {
         F acc = F::mul(mulL1, mulL2);                                // denH1, denH2

@@ -196,6 +196,7 @@ static constexpr int PLONK_PAD = 8;
 //   int divzh(uint64_t n, const F* t, const F* tz, F* out);  void tsplit(uint64_t n, const F* t, const F& b10, const F& b11, F* T1, F* T2, F* T3);
 //   void make_pow(const F& base, uint64_t count, PlonkPow<F>& out, int slot);           // tables in backend memory
 //   F eval(const F* f, uint64_t len, const PlonkPow<F>& pw, F* g, F* P);                // sum f[k] x^k
+//   void mark(int round);                                                               // end of round 1..5 (timing hook; may be a no-op)
 //   int quotient(const F* f_or_null, const PlonkLinIn*, const PlonkLin<F>*, uint64_t n, uint64_t len, uint64_t m, const F& sub0,
 //                const PlonkPow<F>& pw, const PlonkPow<F>& ipw, F* g, F* P, F* q_plain); // f / (X - b) -> plain scalars
 //   int commit_plain(const F* scal_plain, uint64_t len, uint8_t* affine);
@@ -244,6 +245,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
             int rc = be.commit(cs[j], n + 2, pts[j]); if (rc) return rc;
         }
     }
+    be.mark(1);
     // ---------------- round 2 (:315-458)
     PlonkTranscript<PQ, PR> tr;
     std::vector<F> pubA(k.nPublic);
@@ -267,6 +269,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
         be.blind(w.cZ, n, bf, 3);
         int rc = be.commit(w.cZ, n + 3, pt_Z); if (rc) return rc;
     }
+    be.mark(2);
     // ---------------- round 3 (:460-684)
     tr.reset(); tr.add_scalar(r.beta); tr.add_scalar(r.gamma); tr.add_point(pt_Z);
     r.alpha = tr.challenge();
@@ -284,6 +287,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
         rc = be.commit(w.T2, n + 1, pt_T2); if (rc) return rc;
         rc = be.commit(w.T3, n + 6, pt_T3); if (rc) return rc;
     }
+    be.mark(3);
     // ---------------- round 4 (:686-708)
     tr.reset(); tr.add_scalar(r.alpha); tr.add_point(pt_T1); tr.add_point(pt_T2); tr.add_point(pt_T3);
     const F xi = tr.challenge();
@@ -295,6 +299,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
     const F es1 = be.eval(k.s_coef[0], n, pxi, w.g, w.P), es2 = be.eval(k.s_coef[1], n, pxi, w.g, w.P);
     const F ezw = be.eval(w.cZ, n + 3, pxiw, w.g, w.P);
     { const F evs[6] = {ea, eb, ec, es1, es2, ezw}; memcpy(ev_out, evs, sizeof evs); }
+    be.mark(4);
     // ---------------- round 5 (:710-888)
     tr.reset(); tr.add_scalar(xi); tr.add_scalar(ea); tr.add_scalar(eb); tr.add_scalar(ec); tr.add_scalar(es1); tr.add_scalar(es2); tr.add_scalar(ezw);
     PlonkLin<F> L;
@@ -343,6 +348,7 @@ int plonk_prove_flow(B& be, const PlonkKeyView<Fp<PR>>& k, PlonkWork<Fp<PR>>& w,
         if (flag) { err = "Polynomial is not divisible"; return 4; }
         rc = be.commit_plain(w.scal, n + 3, pt_Wxiw); if (rc) return rc;
     }
+    be.mark(5);
     return 0;
 }
 

@@ -23,6 +23,7 @@ template <class F> struct HostBackend {
     std::vector<std::vector<F>> pow_store;
     std::string err;
 
+    void mark(int) {}
     void upload(F* dst, const F* host, size_t n) { memcpy(dst, host, n * sizeof(F)); }
     void download(F* host, const F* src, size_t n) { memcpy(host, src, n * sizeof(F)); }
     void zero(F* p, size_t n) { memset(p, 0, n * sizeof(F)); }
