@@ -1,7 +1,7 @@
 """First PLONK timing on the B200 (planning data, not the headline bench): synthetic satisfiable circuits built by
 oracle/plonk.py's setup on unstructured points, proofs through sb_plonk_prove with the witness in host memory.
 Appends one JSON line per size to gpurun_out/plonk_bench.jsonl as soon as it is measured.
-usage: python profiles/bench_plonk.py [budget_seconds] [log2 sizes ...]"""
+usage: python profiles/bench_plonk.py [plonk|fflonk] [budget_seconds] [log2 sizes ...]"""
 import json
 import os
 import sys
@@ -15,12 +15,18 @@ import snarkjs_b200                     # noqa: E402
 from oracle import oracle as orc        # noqa: E402
 from oracle import plonk as op          # noqa: E402
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 45.0
-sizes = [int(a) for a in sys.argv[2:]] or [14, 16, 18]
+from oracle import fflonk as off       # noqa: E402
+
+argv = sys.argv[1:]
+proto = argv.pop(0) if argv and argv[0] in ("plonk", "fflonk") else "plonk"
+budget = float(argv[0]) if argv else 45.0
+sizes = [int(a) for a in argv[1:]] or [14, 16, 18]
+mod = snarkjs_b200.plonk if proto == "plonk" else snarkjs_b200.fflonk
+n_blinders = 11 if proto == "plonk" else 9
 os.makedirs("gpurun_out", exist_ok=True)
 curve = snarkjs_b200.getCurveFromName("bn128")
 ci = orc.CURVES[orc.BN254]
-bl = b"".join(ci.fr_to_mont(7 + i) for i in range(11))
+bl = b"".join(ci.fr_to_mont(7 + i) for i in range(n_blinders))
 est = {14: 6, 16: 14, 18: 45, 20: 200}
 for lg in sizes:
     if time.time() - T0 + est.get(lg, 10) > budget:
@@ -28,11 +34,12 @@ for lg in sizes:
         continue
     t = time.time()
     gates, adds, n_vars, n_pub, wit = op.chain_gates((1 << lg) - 6)
-    zkey = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=4242, structured=False)
+    setup = op.plonk_setup_synth if proto == "plonk" else off.fflonk_setup_synth
+    zkey = setup(gates, adds, n_vars, n_pub, tau=4242, structured=False)
     t_setup = time.time() - t
     W = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in wit), np.uint8)
     t = time.time()
-    pk = snarkjs_b200.plonk.ProvingKey(zkey, curve)
+    pk = mod.ProvingKey(zkey, curve)
     t_load = time.time() - t
     del zkey
     first = pk.prove_raw(W, bl)
@@ -47,7 +54,7 @@ for lg in sizes:
         rounds.append([curve.last_ms(i) for i in range(1, 6)])
     launches = (curve.launch_count() - l0) // reps
     assert raw == first
-    line = {"what": "plonk_prove", "curve": "bn128", "log2_domain": lg, "n_public": n_pub, "n_additions": len(adds),
+    line = {"what": proto + "_prove", "curve": "bn128", "log2_domain": lg, "n_public": n_pub, "n_additions": len(adds),
             "ms_e2e_median": round(float(np.median(ms)), 3), "ms_min": round(min(ms), 3), "proofs_per_s": round(1e3 / float(np.median(ms)), 2),
             "ms_flow_device_clock": round(float(np.median(dev)), 3), "launches_per_proof": int(launches),
             "ms_rounds_1_to_5": [round(float(x), 3) for x in np.median(np.array(rounds), axis=0)],
