@@ -456,6 +456,18 @@ def plonk_prove(zkey, wtns, blinders: Sequence[int], return_parts: bool = False)
     w4n = _fr_w(ci, power + 2)
     T = [0] * (4 * n)
     Tz = [0] * (4 * n)
+    def mul4(a, bb, c, d, ap, bp, cp, dp, p):                                                    # mul_z.js:104-147
+        a_b, a_bp, ap_b, ap_bp = a * bb % r, a * bp % r, ap * bb % r, ap * bp % r
+        c_d, c_dp, cp_d, cp_dp = c * d % r, c * dp % r, cp * d % r, cp * dp % r
+        rr = a_b * c_d % r
+        rz = (ap_b * c_d + a_bp * c_d + a_b * cp_d + a_b * c_dp) % r
+        if p:
+            a1 = (ap_bp * c_d + ap_b * cp_d + ap_b * c_dp + a_bp * cp_d + a_bp * c_dp + a_b * cp_dp) % r
+            a2 = (a_bp * cp_dp + ap_b * cp_dp + ap_bp * c_dp + ap_bp * cp_d) % r
+            a3 = ap_bp * cp_dp % r
+            rz = (rz + Z1[p] * a1 + Z2[p] * a2 + Z3[p] * a3) % r
+        return rr, rz
+
     w = 1
     for i in range(4 * n):
         a_, b_, c_, z_ = evA[i], evB[i], evC[i], evZ[i]
@@ -481,22 +493,8 @@ def plonk_prove(zkey, wtns, blinders: Sequence[int], return_parts: bool = False)
         e1 = (e1 * qm + a_ * ql + b_ * qr_ + c_ * qo + pi + qc) % r
         e1z = (e1z * qm + ap * ql + bp * qr_ + cp * qo) % r
         betaw = beta * w % r
-
-        def mul4(a, bb, c, d, dp):                                                               # mul_z.js:104-147
-            a_b, a_bp, ap_b, ap_bp = a * bb % r, a * bp % r, ap * bb % r, ap * bp % r
-            c_d, c_dp, cp_d, cp_dp = c * d % r, c * dp % r, cp * d % r, cp * dp % r
-            rr = a_b * c_d % r
-            a0 = (ap_b * c_d + a_bp * c_d + a_b * cp_d + a_b * c_dp) % r
-            rz = a0
-            if p:
-                a1 = (ap_bp * c_d + ap_b * cp_d + ap_b * c_dp + a_bp * cp_d + a_bp * c_dp + a_b * cp_dp) % r
-                a2 = (a_bp * cp_dp + ap_b * cp_dp + ap_bp * c_dp + ap_bp * cp_d) % r
-                a3 = ap_bp * cp_dp % r
-                rz = (rz + Z1[p] * a1 + Z2[p] * a2 + Z3[p] * a3) % r
-            return rr, rz
-
-        e2, e2z = mul4((a_ + betaw + gamma) % r, (b_ + betaw * k1 + gamma) % r, (c_ + betaw * k2 + gamma) % r, z_, zp)
-        e3, e3z = mul4((a_ + beta * s1 + gamma) % r, (b_ + beta * s2 + gamma) % r, (c_ + beta * s3 + gamma) % r, zw_, zWp)
+        e2, e2z = mul4((a_ + betaw + gamma) % r, (b_ + betaw * k1 + gamma) % r, (c_ + betaw * k2 + gamma) % r, z_, ap, bp, cp, zp, p)
+        e3, e3z = mul4((a_ + beta * s1 + gamma) % r, (b_ + beta * s2 + gamma) % r, (c_ + beta * s3 + gamma) % r, zw_, ap, bp, cp, zWp, p)
         l1 = lag_ev[0][i]
         e4 = (z_ - 1) * l1 % r * alpha2 % r
         e4z = zp * l1 % r * alpha2 % r
