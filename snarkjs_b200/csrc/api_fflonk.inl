@@ -25,6 +25,7 @@ struct FflonkKeyDev {
     void* work[32] = {nullptr};                  // order of FflonkWork
     void* d_cub = nullptr; size_t cub_bytes = 0;
     int* d_flag = nullptr; void* d_red = nullptr;
+    bool c0_is_interleave = false;
     void* commit_scratch() const { return work[31]; }   // FflonkWork::scal
 };
 
@@ -108,6 +109,7 @@ template <class PR> int fflonk_load_impl(sb_ctx* c, const uint8_t* zkey, uint64_
     FflonkKeyDev* k = new FflonkKeyDev();
     k->hdr.assign(z.sec[2].p, z.sec[2].p + z.sec[2].len);
     k->z = z;
+    k->c0_is_interleave = fflonk_c0_is_interleave(z);
     { const ptrdiff_t d = k->hdr.data() - z.sec[2].p;
       k->z.q += d; k->z.r += d; k->z.k1 += d; k->z.k2 += d; k->z.w3 += d; k->z.w4 += d; k->z.w8 += d; k->z.wr += d; k->z.X_2 += d; k->z.C0 += d; }
     for (auto& s : k->z.sec) s = PlonkZkey::Sec();
@@ -190,7 +192,7 @@ template <class PQ, class PR> int fflonk_prove_impl(sb_ctx* c, FflonkKeyDev* kd,
     k.add_sig = kd->d_add_sig; k.add_fac = (const F*)kd->d_add_fac; k.add_order = kd->d_add_order; k.level_end = kd->level_end;
     for (int j = 0; j < 3; j++) { k.map[j] = kd->d_map[j]; k.s_coef[j] = (const F*)kd->d_s_coef[j]; k.s_ev[j] = (const F*)kd->d_s_ev[j]; }
     for (int j = 0; j < 5; j++) { k.q_coef[j] = (const F*)kd->d_q_coef[j]; k.q_ev[j] = (const F*)kd->d_q_ev[j]; }
-    k.lag = (const F*)kd->d_lag; k.c0 = (const F*)kd->d_c0;
+    k.lag = (const F*)kd->d_lag; k.c0 = (const F*)kd->d_c0; k.c0_is_interleave = kd->c0_is_interleave;
     PlonkPow<F>* tabs[3] = {&k.wpow, &k.w2pow, &k.w4pow};
     for (int t = 0; t < 3; t++) { tabs[t]->lo = (const F*)kd->d_wtab[t][0]; tabs[t]->hi = (const F*)kd->d_wtab[t][1]; tabs[t]->h = kd->wtab_h[t]; }
     FflonkWork<F> w;

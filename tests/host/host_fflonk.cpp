@@ -61,6 +61,7 @@ static int prove_impl(void* so, int curve, const FflonkZkey& z, const uint8_t* w
     for (uint32_t j = 0; j < nl; j++) memcpy(lag.data() + (size_t)j * 4 * n, z.sec[15].p + 160 * n * j + 32 * n, 128 * n);
     k.lag = lag.data();
     memcpy(c0.data(), z.sec[17].p, 256 * n); k.c0 = c0.data();
+    k.c0_is_interleave = fflonk_c0_is_interleave(z);
     be.make_pow(k.wn, n, k.wpow, 0);
     be.make_pow(w2n, 2 * n, k.w2pow, 0);
     be.make_pow(w4n, 4 * n, k.w4pow, 0);

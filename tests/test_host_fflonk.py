@@ -70,6 +70,22 @@ def test_host_fflonk_synthetic(hostlib, n_gates, n_pub, with_additions):
         assert fflonk.fflonk_verify(fflonk.fflonk_vk(zkey), public, got)
 
 
+def test_host_fflonk_c0_section_not_the_interleave(hostlib):
+    """The opening values of C0 are derived from ql..s3 only when section 17 equals the interleave of sections 7-14 (checked
+    at load); a key whose section 17 differs takes the reference's direct evaluations instead.  Either way: oracle parity."""
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(40)
+    zkey = bytearray(fflonk.fflonk_setup_synth(gates, adds, n_vars, n_pub, tau=77))
+    data, secs = orc.read_binfile(bytes(zkey), "zkey", 2)
+    pos = secs[17][0][0] + 5 * 32                       # one coefficient of C0
+    zkey[pos] ^= 1
+    wtns = plonk.wtns_bytes(wit)
+    rc, err, raw = host_prove(hostlib, bytes(zkey), wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = fflonk.fflonk_prove(bytes(zkey), wtns, BLINDERS)
+    assert proof_from_bytes(raw) == want
+    assert not fflonk.fflonk_verify(fflonk.fflonk_vk(bytes(zkey)), public, want)   # such a key cannot produce valid proofs
+
+
 def test_host_fflonk_errors(hostlib, golden):
     g = golden("fflonk_case.npz")
     zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
