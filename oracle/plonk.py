@@ -32,7 +32,8 @@ Pins (tests/test_oracle_plonk.py), and what is NOT pinned:
     S1x twice instead of S1x,S1y and accumulates T3 twice).  PLONK prover parity is therefore "partially pinned".
 
 Field elements are plain Python ints in [0, r) inside this file; bulk NTT / MSM go through the C++ restatement
-(oracle.fr_fft, oracle.multiexp_affine), whose own pins are the zkey/ptau fixtures.  BN254 only (the pairing is).
+(oracle.fr_fft, oracle.multiexp_affine), whose own pins are the zkey/ptau fixtures.  Prover: both curves; verifier: BN254
+through oracle.py's pairing, BLS12-381 through oracle/pairing_bls.py.
 """
 from __future__ import annotations
 
@@ -266,10 +267,14 @@ def _challenges(ci, vk, pub: Sequence[int], pr) -> Dict:
 
 def plonk_verify(vk_json: Dict, public_signals: Sequence, proof_json: Dict) -> bool:
     """src/plonk_verify.js:29-124 on JSON-shaped inputs (decimal strings)."""
-    ci = orc.CURVES[orc.BN254]
-    if vk_json.get("curve", "bn128") != "bn128":
-        raise NotImplementedError("python pairing is BN254-only")
-    r, q = ci.r, ci.q
+    if vk_json.get("curve", "bn128") == "bn128":
+        ci = orc.CURVES[orc.BN254]
+        _add, _mul, _neg, _g1_valid, pairing = orc._g1_add_int, orc._g1_mul_int, globals()["_neg"], globals()["_g1_valid"], orc.pairing_product_is_one
+    else:                                   # bls12381: same verifier, its own G1 arithmetic and pairing
+        from . import pairing_bls as pb
+        ci = orc.CURVES[orc.BLS12_381]
+        _add, _mul, _neg, _g1_valid, pairing = pb.g1_add, pb.g1_mul, pb.g1_neg, pb.g1_valid, pb.pairing_product_is_one
+    r = ci.r
     pr = {k: _g1(proof_json[k]) for k in ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")}
     evals_raw = {k: int(proof_json[k]) for k in ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw")}
     vk = {k: _g1(vk_json[k]) for k in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3")}
@@ -333,7 +338,7 @@ def plonk_verify(vk_json: Dict, public_signals: Sequence, proof_json: Dict) -> b
     B1 = _add(_add(B1, F), _neg(E))
     if A1 is None or B1 is None:
         return A1 is None and B1 is None
-    return orc.pairing_product_is_one([(_neg(A1), X_2), (B1, ci.g2)])
+    return pairing([(_neg(A1), X_2), (B1, ci.g2)])
 
 
 # ----------------------------------------------------------------------------- prover

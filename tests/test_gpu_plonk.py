@@ -94,7 +94,7 @@ def test_plonk_deep_addition_chain(env):
 
 
 def test_plonk_bls12381(env):
-    """BLS12-381: 12-limb base field (transcript, MSM), its own Fr roots; parity with the oracle (no pairing check)."""
+    """BLS12-381: 12-limb base field (transcript, MSM), its own Fr roots; parity with the oracle, and the proof verifies."""
     sb, op, orc = env["sb"], env["op"], env["orc"]
     ci = orc.CURVES[orc.BLS12_381]
     gates, adds, n_vars, n_pub, wit = op.chain_gates(120, r=ci.r)
@@ -107,6 +107,7 @@ def test_plonk_bls12381(env):
         pk.release()
         want, wpub = op.plonk_prove(zkey, wtns, BLINDERS)
         assert (proof, public) == (want, wpub)
+        assert op.plonk_verify(op.plonk_vk(zkey), public, proof)
     finally:
         curve.terminate()
 

@@ -114,8 +114,9 @@ def test_host_flow_bls12381(hostlib):
     wtns = plonk.wtns_bytes(wit, ci.r)
     rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS, ci)
     assert rc == 0, err
-    want, _ = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    want, public = plonk.plonk_prove(zkey, wtns, BLINDERS)
     assert proof_from_bytes(raw, ci) == want
+    assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, want)        # BLS12-381 pairing: oracle/pairing_bls.py
 
 
 def test_host_flow_errors(hostlib):

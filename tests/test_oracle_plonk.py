@@ -70,3 +70,28 @@ def test_synthetic_setup_prove_verify(n_gates):
     wit2[3] = (wit2[3] + 1) % orc.P_BN_R
     with pytest.raises(ValueError):
         plonk.plonk_prove(zkey, plonk.wtns_bytes(wit2), BLINDERS)
+
+
+def test_bls12381_pairing_is_bilinear():
+    from oracle import pairing_bls as pb
+    ci = orc.CURVES[orc.BLS12_381]
+    g2 = orc.g_from_affine(ci.id, 2, ci.g2_affine_bytes(ci.g2))
+    a, b = 0x1234567, 0x89ABCDE
+    bq = ci.g2_from_affine_bytes(bytes(orc.g_to_affine(ci.id, 2, orc.g_times(ci.id, 2, g2, b.to_bytes(32, "little"))))[:4 * ci.n8q])
+    ap = pb.g1_mul(ci.g1, a)
+    assert pb.g1_valid(ap)
+    assert pb.pairing_product_is_one([(ap, bq), (pb.g1_neg(pb.g1_mul(ci.g1, a * b % ci.r)), ci.g2)])
+    assert not pb.pairing_product_is_one([(ap, bq), (pb.g1_neg(pb.g1_mul(ci.g1, (a * b + 1) % ci.r)), ci.g2)])
+
+
+def test_plonk_on_bls12381_verifies():
+    ci = orc.CURVES[orc.BLS12_381]
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(60, r=ci.r, n_pub=2)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=99991, curve=orc.BLS12_381)
+    proof, public = plonk.plonk_prove(zkey, plonk.wtns_bytes(wit, ci.r), BLINDERS)
+    vk = plonk.plonk_vk(zkey)
+    assert vk["curve"] == "bls12381" and plonk.plonk_verify(vk, public, proof)
+    bad = dict(proof)
+    bad["eval_c"] = str((int(proof["eval_c"]) + 1) % ci.r)
+    assert not plonk.plonk_verify(vk, public, bad)
+    assert not plonk.plonk_verify(vk, [public[1], public[0]], proof)
