@@ -874,11 +874,14 @@ def _g1_mul_int(p, k):
 
 
 def groth16_verify(vk: dict, public_signals: List[int], proof: dict) -> bool:
-    """src/groth16_verify.js:25-85 (BN254): public inputs must be < r (aliasing check :41-46), then
-    e(-A,B) e(alpha,beta) e(vk_x,gamma) e(C,delta) == 1."""
+    """src/groth16_verify.js:25-85: public inputs must be < r (aliasing check :41-46), then
+    e(-A,B) e(alpha,beta) e(vk_x,gamma) e(C,delta) == 1.  BN254 through the pairing above, BLS12-381 through pairing_bls.py."""
     ci: CurveInfo = vk["curve"]
-    if ci.id != BN254:
-        raise NotImplementedError("python pairing is BN254-only")
+    if ci.id == BN254:
+        add, mul, pairing, q, b = _g1_add_int, _g1_mul_int, pairing_product_is_one, _Q, 3
+    else:
+        from . import pairing_bls as pb
+        add, mul, pairing, q, b = pb.g1_add, pb.g1_mul, pb.pairing_product_is_one, pb.Q, 4
     if len(public_signals) != vk["nPublic"]:
         return False
     for s in public_signals:
@@ -886,12 +889,12 @@ def groth16_verify(vk: dict, public_signals: List[int], proof: dict) -> bool:
             return False
     cpub = vk["IC"][0]
     for i, s in enumerate(public_signals):
-        cpub = _g1_add_int(cpub, _g1_mul_int(vk["IC"][i + 1], int(s)))
+        cpub = add(cpub, mul(vk["IC"][i + 1], int(s)))
     A = (int(proof["pi_a"][0]), int(proof["pi_a"][1]))
     B = ((int(proof["pi_b"][0][0]), int(proof["pi_b"][0][1])), (int(proof["pi_b"][1][0]), int(proof["pi_b"][1][1])))
     C = (int(proof["pi_c"][0]), int(proof["pi_c"][1]))
-    negA = (A[0], (-A[1]) % _Q)
+    negA = (A[0], (-A[1]) % q)
     # on-curve checks (G1.isValid / G2.isValid :48-63)
-    if (A[1] * A[1] - A[0] ** 3 - 3) % _Q or (C[1] * C[1] - C[0] ** 3 - 3) % _Q:
+    if (A[1] * A[1] - A[0] ** 3 - b) % q or (C[1] * C[1] - C[0] ** 3 - b) % q:
         return False
-    return pairing_product_is_one([(negA, B), (vk["alpha1"], vk["beta2"]), (cpub, vk["gamma2"]), (C, vk["delta2"])])
+    return pairing([(negA, B), (vk["alpha1"], vk["beta2"]), (cpub, vk["gamma2"]), (C, vk["delta2"])])
