@@ -10,11 +10,16 @@ What it restates (reference file:line):
                                  163-184, 218-296, 592-660, 970-977), Evaluations (src/polynomial/evaluations.js:29-36)
                                  and MulZ (src/mul_z.js:20-148)
   * the PLONK zkey layout        src/zkey_utils.js:261-299, src/plonk_constants.js:1-15, src/plonk_setup.js:99-480
+  * plonkSetup                   src/plonk_setup.js:36-510 (plonk_setup: from an r1cs and a prepared ptau)
   * a *synthetic* structured setup (plonk_setup_synth): same sections as plonk_setup.js writes, from directly-given
     gates and a known tau (the reference derives the gates from an r1cs and the points from a ptau file)
 
 Pins (tests/test_oracle_plonk.py), and what is NOT pinned:
   * Keccak-256 against the published known answers ("" and "abc").
+  * plonk_setup(r1cs, prepared ptau) reproduces BYTE FOR BYTE the two PLONK zkeys the reference ships — test/plonk_circuit/
+    circuit.zkey (14 748 bytes) and test/circuit2/circuit.zkey (4 160 728 bytes: domain 2048, 1001 additions, 4 public
+    signals): gate derivation, additions, wire maps, selector / sigma / Lagrange sections, commitments, header.  This pins the
+    key layout the prover reads and everything plonk_setup_synth shares with it.
   * plonk_vk(test/plonk_circuit/circuit.zkey) == the reference's verification_key.json (header layout, Fr.w[power]).
   * a proof made here from the reference's own circuit.zkey + witness.wtns verifies with the reference's
     verification key, and stops verifying when any proof field or public signal is perturbed; the same holds for keys
@@ -752,3 +757,157 @@ def wtns_bytes(wit: Sequence[int], r: int = orc.P_BN_R) -> bytes:
     """wtns container (src/wtns_utils.js:24-60)."""
     hdr = struct.pack("<I", 32) + r.to_bytes(32, "little") + struct.pack("<I", len(wit))
     return orc.write_binfile("wtns", 2, [(1, hdr), (2, b"".join(int(x).to_bytes(32, "little") for x in wit))])
+
+
+# ----------------------------------------------------------------------------- plonk setup from an r1cs and a prepared ptau
+def plonk_gates_from_r1cs(r1: Dict, r: int):
+    """processConstraints (src/plonk_setup.js:142-299): r1cs constraints -> PLONK gates (sl, sr, so, qm, ql, qr, qo, qc) and
+    additions, including the reference's behaviour on JavaScript objects: linear combinations are keyed by signal (a repeated
+    signal overwrites), iterate in ascending signal order, and a zero coefficient is never dropped (`x == 0n` is false for the
+    byte-array field elements, :147-149, 189-191)."""
+    n_pub = r1["nOutputs"] + r1["nPubInputs"]
+    state = {"nvars": r1["nVars"]}
+    gates, additions = [], []
+
+    def as_lc(terms):
+        return {int(s): int(v) % r for s, v in terms}
+
+    def lc_type(lc):                                                                 # :258-274
+        n = sum(1 for s in lc if s != 0)
+        if n > 0:
+            return str(n)
+        return "k" if 0 in lc else "0"
+
+    def join(lc1, k, lc2):                                                          # :151-173
+        res = {}
+        for s in sorted(lc1):
+            res[s] = (res.get(s, 0) + k * lc1[s]) % r
+        for s in sorted(lc2):
+            res[s] = (res.get(s, 0) - lc2[s]) % r
+        return res
+
+    def reduce_coefs(lc, max_c):                                                    # :175-220
+        k = 0
+        cs = []
+        for s in sorted(lc):
+            if s == 0:
+                k = (k + lc[s]) % r
+            else:
+                cs.append([s, lc[s]])
+        while len(cs) > max_c:
+            c1, c2 = cs.pop(0), cs.pop(0)
+            so = state["nvars"]
+            state["nvars"] += 1
+            gates.append((c1[0], c2[0], so, 0, (-c1[1]) % r, (-c2[1]) % r, 1, 0))
+            additions.append((c1[0], c2[0], c1[1], c2[1]))
+            cs.append([so, 1])
+        ss = [c[0] for c in cs] + [0] * (max_c - len(cs))
+        cf = [c[1] for c in cs] + [0] * (max_c - len(cs))
+        return k, ss, cf
+
+    def add_sum(lc):                                                                # :222-233
+        k, ss, cf = reduce_coefs(lc, 3)
+        gates.append((ss[0], ss[1], ss[2], 0, cf[0], cf[1], cf[2], k))
+
+    def add_mul(la, lb, lc):                                                        # :235-256
+        ka, sa, ca = reduce_coefs(la, 1)
+        kb, sb_, cb = reduce_coefs(lb, 1)
+        kc, sc, cc = reduce_coefs(lc, 1)
+        gates.append((sa[0], sb_[0], sc[0], ca[0] * cb[0] % r, ca[0] * kb % r, ka * cb[0] % r, (-cc[0]) % r, (ka * kb - kc) % r))
+
+    for s in range(1, n_pub + 1):                                                   # :285-297
+        gates.append((s, 0, 0, 0, 1, 0, 0, 0))
+    for la, lb, lc in r1["constraints"]:                                            # :276-283, 299-302
+        la, lb, lc = as_lc(la), as_lc(lb), as_lc(lc)
+        ta, tb = lc_type(la), lc_type(lb)
+        if ta == "0" or tb == "0":
+            add_sum(lc)
+        elif ta == "k":
+            add_sum(join(lb, la[0], lc))
+        elif tb == "k":
+            add_sum(join(la, lb[0], lc))
+        else:
+            add_mul(la, lb, lc)
+    return gates, additions, state["nvars"], n_pub
+
+
+def plonk_setup(r1cs, ptau) -> bytes:
+    """src/plonk_setup.js:36-480 from an r1cs and a prepared ptau: the zkey the reference writes, byte for byte (sections in the
+    reference's order 3..14, 1, 2).  Pinned by tests/test_oracle_plonk.py against test/plonk_circuit/circuit.zkey."""
+    r1 = orc.read_r1cs(r1cs)
+    pdata, psecs = orc.read_binfile(ptau, "ptau", 1)
+    ph = orc.read_ptau_header(pdata, psecs)
+    ci = orc.curve_from_q(ph["q"])
+    r = ci.r
+    if r1["prime"] != r:
+        raise ValueError("r1cs curve does not match powers of tau ceremony curve")
+    gates, additions, n_vars, n_public = plonk_gates_from_r1cs(r1, r)
+    ng = len(gates)
+    power = max(3, (ng - 1).bit_length())                                           # :74-76
+    if power > ph["power"]:
+        raise ValueError("circuit too big for this power of tau ceremony")
+    if 12 not in psecs:
+        raise ValueError("Powers of tau is not prepared.")
+    n = 1 << power
+    sG1, sG2 = 2 * ci.n8q, 4 * ci.n8q
+
+    def psec(sid, lo, hi):
+        p, _ = psecs[sid][0]
+        return bytes(pdata[p + lo:p + hi])
+
+    lpoints = psec(12, (n - 1) * sG1, (2 * n - 1) * sG1)                            # :86-88
+    wn = _fr_w(ci, power)
+    k1 = 2
+    while pow(k1, n, r) == 1:                                                       # getK1K2 :482-503 (membership of <w> is k^n == 1)
+        k1 += 1
+    k2 = k1 + 1
+    while pow(k2, n, r) == 1 or pow(k2 * pow(k1, -1, r) % r, n, r) == 1:
+        k2 += 1
+    secs = [(3, b"".join(struct.pack("<II", a[0], a[1]) + ci.fr_to_mont(a[2]) + ci.fr_to_mont(a[3]) for a in additions))]
+    for pos in range(3):
+        secs.append((4 + pos, np.array([g[pos] for g in gates], dtype="<u4").tobytes()))
+
+    def p4(evals_mont: bytes) -> bytes:                                             # writeP4 :331-338
+        coef = bytes(orc.fr_fft(ci.id, evals_mont, True))
+        return coef + bytes(orc.fr_fft(ci.id, coef + bytes(3 * n * 32), False))
+
+    def commit_evals(evals_mont: bytes):                                            # multiExpAffine(LPoints, fromMontgomery(Q)) :326-329
+        jac = orc.multiexp_affine(ci.id, 1, lpoints, bytes(orc.batch_convert(ci.fr, False, evals_mont)))
+        return bytes(orc.g_to_affine(ci.id, 1, jac))[:sG1]
+
+    vk = {}
+    for pos, (sid, name) in enumerate(((7, "Qm"), (8, "Ql"), (9, "Qr"), (10, "Qo"), (11, "Qc"))):
+        ev = _mont_from_ints(ci, [g[3 + pos] for g in gates] + [0] * (n - ng))
+        secs.append((sid, p4(ev)))
+        vk[name] = commit_evals(ev)
+    sigma = [0] * (3 * n)                                                           # writeSigma :362-438
+    last: Dict[int, int] = {}
+    first: Dict[int, int] = {}
+    w = 1
+    for i in range(n):
+        for col in range(3):
+            s = gates[i][col] if i < ng else 0
+            p = col * n + i
+            if s not in last:
+                first[s] = p
+            else:
+                sigma[p] = last[s]
+            last[s] = w if col == 0 else (w * k1 % r if col == 1 else w * k2 % r)
+        w = w * wn % r
+    for s, p in first.items():
+        sigma[p] = last[s]
+    payload = b""
+    for col, name in enumerate(("S1", "S2", "S3")):
+        ev = _mont_from_ints(ci, sigma[col * n:(col + 1) * n])
+        payload += p4(ev)
+        vk[name] = commit_evals(ev)
+    secs.append((12, payload))
+    secs.append((13, b"".join(p4(_mont_from_ints(ci, [1 if j == i else 0 for j in range(n)])) for i in range(max(n_public, 1)))))
+    secs.append((14, psec(2, 0, (n + 6) * sG1)))                                    # :122-127
+    hdr = struct.pack("<I", ci.n8q) + ci.q.to_bytes(ci.n8q, "little") + struct.pack("<I", 32) + r.to_bytes(32, "little")
+    hdr += struct.pack("<IIIII", n_vars, n_public, n, len(additions), ng)
+    hdr += ci.fr_to_mont(k1) + ci.fr_to_mont(k2)
+    for name in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+        hdr += vk[name]
+    hdr += psec(3, sG2, 2 * sG2)                                                    # X_2 = tau * G2 (:477-479)
+    return orc.write_binfile("zkey", 1, secs + [(1, struct.pack("<I", 2)), (2, hdr)])

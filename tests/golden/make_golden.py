@@ -112,6 +112,30 @@ def plonk_case():
     print("plonk_case:", {k: v.size for k, v in out.items()})
 
 
+def plonk_setup_cases():
+    """Inputs of `plonk setup` for the two PLONK keys the reference ships (test/plonk_circuit: domain 8; test/circuit2: domain
+    2048, 1001 additions, 4 public signals), with the sha256 of the zkey the reference produced from them: the r1cs, the
+    witness, and the slices of the prepared ptau that src/plonk_setup.js reads (section 2 first n + 6 points, section 3 first
+    two points, section 12 Lagrange points of the domain)."""
+    import hashlib
+    ptau = f"{REF}/plonk_circuit/powersOfTau15_final.ptau"
+    pdata, psecs = O.read_binfile(ptau, "ptau", 1)
+    out = {"ptau_header": u8(bytes(O.section(pdata, psecs, 1)))}
+    for tag, d in (("c8", f"{REF}/plonk_circuit"), ("c2048", f"{REF}/circuit2")):
+        zkey = open(f"{d}/circuit.zkey", "rb").read()
+        zdata, zsecs = O.read_binfile(zkey, "zkey", 2)
+        n = O.read_zkey_header(zdata, zsecs)["domainSize"]
+        out[f"{tag}_r1cs"] = u8(open(f"{d}/circuit.r1cs", "rb").read())
+        out[f"{tag}_wtns"] = u8(open(f"{d}/witness.wtns", "rb").read())
+        out[f"{tag}_zkey_sha256"] = u8(hashlib.sha256(zkey).digest())
+        out[f"{tag}_n"] = np.array([n], dtype=np.uint32)
+        out[f"{tag}_ptau2"] = u8(bytes(O.section(pdata, psecs, 2)[:(n + 6) * 64]))
+        out[f"{tag}_ptau12"] = u8(bytes(O.section(pdata, psecs, 12)[(n - 1) * 64:(2 * n - 1) * 64]))
+    out["ptau3"] = u8(bytes(O.section(pdata, psecs, 3)[:256]))
+    np.savez_compressed(os.path.join(HERE, "plonk_setup_cases.npz"), **out)
+    print("plonk_setup_cases:", {k: v.size for k, v in out.items()})
+
+
 def fflonk_case():
     """The reference's fflonk fixture as data (test/fflonk): proving key, witness, verification key, public signals."""
     d = f"{REF}/fflonk"
@@ -122,7 +146,7 @@ def fflonk_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ntt", "msm", "ptau", "groth16", "plonk", "fflonk"]
+    which = sys.argv[1:] or ["ntt", "msm", "ptau", "groth16", "plonk", "fflonk", "plonk_setup"]
     if "ntt" in which:
         ntt_goldens()
     if "msm" in which:
@@ -135,3 +159,5 @@ if __name__ == "__main__":
         plonk_case()
     if "fflonk" in which:
         fflonk_case()
+    if "plonk_setup" in which:
+        plonk_setup_cases()

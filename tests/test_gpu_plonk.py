@@ -80,6 +80,20 @@ def test_plonk_shapes(env, n_gates, n_pub, with_additions):
 
 
 @pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
+def test_plonk_reference_circuit2(env, golden, reference_plonk_key):
+    """The reference's larger PLONK key (test/circuit2: domain 2048, 1001 additions, 4 public signals; rebuilt byte for byte
+    from its r1cs) with the reference's own witness."""
+    zkey, wtns = reference_plonk_key(golden("plonk_setup_cases.npz"), "c2048")
+    pk = env["sb"].plonk.ProvingKey(zkey, env["curve"])
+    try:
+        proof, public = env["sb"].plonk.prove(pk, wtns, env["bl"])
+        assert (proof, public) == env["op"].plonk_prove(zkey, wtns, BLINDERS)
+        assert len(public) == 4 and env["op"].plonk_verify(env["op"].plonk_vk(zkey), public, proof)
+    finally:
+        pk.release()
+
+
+@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
 def test_plonk_deep_addition_chain(env):
     """Every addition depends on the previous one: one k_pl_additions launch per addition (dependency levels)."""
     op = env["op"]

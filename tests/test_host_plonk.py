@@ -93,6 +93,16 @@ def test_host_flow_shapes(hostlib, n_gates, n_pub, with_additions):
     assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, got)
 
 
+def test_host_flow_reference_circuit2(hostlib, golden, reference_plonk_key):
+    """The reference's larger PLONK key (test/circuit2: domain 2048, 1001 additions, 4 public signals), rebuilt byte for byte
+    from its r1cs, with the reference's own witness."""
+    zkey, wtns = reference_plonk_key(golden("plonk_setup_cases.npz"), "c2048")
+    rc, err, raw = host_prove(hostlib, zkey, wtns, BLINDERS)
+    assert rc == 0, err
+    want, public = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    assert len(public) == 4 and proof_from_bytes(raw) == want
+
+
 def test_host_flow_deep_addition_chain(hostlib):
     """Additions that each depend on the previous one: one dependency level per addition (plonk_addition_levels must keep
     the reference's sequential semantics, plonk_prove.js:166-211)."""

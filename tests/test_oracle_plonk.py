@@ -95,3 +95,20 @@ def test_plonk_on_bls12381_verifies():
     bad["eval_c"] = str((int(proof["eval_c"]) + 1) % ci.r)
     assert not plonk.plonk_verify(vk, public, bad)
     assert not plonk.plonk_verify(vk, [public[1], public[0]], proof)
+
+
+@pytest.mark.parametrize("tag", ["c8", "c2048"])
+def test_plonk_setup_reproduces_reference_zkeys_byte_for_byte(golden, reference_plonk_key, tag):
+    """oracle.plonk.plonk_setup (r1cs -> gates, additions, selectors, sigma, Lagrange, commitments, header) gives exactly the
+    zkey files the reference ships: test/plonk_circuit/circuit.zkey (14 748 bytes) and test/circuit2/circuit.zkey (4 160 728
+    bytes: domain 2048, 1001 additions, 4 public signals).  This pins the key layout and everything plonk_setup_synth shares."""
+    g = golden("plonk_setup_cases.npz")
+    zkey, wtns = reference_plonk_key(g, tag)
+    if tag == "c8":
+        assert zkey == bytes(golden("plonk_case.npz")["zkey"])
+    # and the prover / verifier work on it (real circom circuit with additions for c2048)
+    proof, public = plonk.plonk_prove(zkey, wtns, BLINDERS)
+    assert plonk.plonk_verify(plonk.plonk_vk(zkey), public, proof)
+    bad = dict(proof)
+    bad["eval_s1"] = str((int(proof["eval_s1"]) + 1) % orc.P_BN_R)
+    assert not plonk.plonk_verify(plonk.plonk_vk(zkey), public, bad)
