@@ -9,8 +9,11 @@ What it restates (reference file:line):
                                  lagrangePolynomialInterpolation :896-930, zerofierPolynomial :932-948
   * fflonkVerify                 src/fflonk_verify.js:29-597
   * the fflonk zkey layout       src/zkey_utils.js:301-339, src/fflonk_constants.js:27-44
+  * fflonkSetup                  src/fflonk_setup.js:59-559, src/r1cs_constraint_processor.js:24-200 (fflonk_setup)
 
-Pins (tests/test_oracle_fflonk.py): fflonk_vk(test/fflonk/circuit.zkey) equals the reference's circuit_vk.json; a proof
+Pins (tests/test_oracle_fflonk.py): fflonk_setup(r1cs, ptau) reproduces test/fflonk/circuit.zkey BYTE FOR BYTE (593 092 bytes:
+gate derivation with 100 additions, selectors, sigmas, Lagrange, PTau, C0, header), which pins the key layout the prover
+reads; fflonk_vk(test/fflonk/circuit.zkey) equals the reference's circuit_vk.json; a proof
 made here from the reference's circuit.zkey + witness.wtns verifies against that verification key and public.json, and
 stops verifying when a commitment, an evaluation or the public signal is perturbed.  Prover and verifier restate two
 different reference files.  The reference ships no fflonk proof and draws its blinders at random (:321-324), so the
@@ -598,3 +601,153 @@ def fflonk_setup_synth(gates, additions, n_vars: int, n_public: int, tau: int, s
     hdr += _g2_times_gen(ci, tau) if structured else ci.g2_affine_bytes(ci.g2)
     hdr += ci.g1_affine_bytes(c0_point)
     return orc.write_binfile("zkey", 1, [(1, struct.pack("<I", 10)), (2, hdr)] + secs)
+
+
+# ----------------------------------------------------------------------------- fflonk setup from an r1cs and a ptau
+def fflonk_gates_from_r1cs(r1: Dict, r: int):
+    """computeFFConstraints (src/fflonk_setup.js:160-209) with src/r1cs_constraint_processor.js:24-200: gates are
+    (s1, s2, so, ql, qr, qm, qo, qc).  Unlike plonk_setup.js, zero coefficients ARE dropped (normalizeLinearCombination uses
+    Fr.isZero, :85-92); linear combinations are keyed by signal and iterate in ascending signal order."""
+    n_pub = r1["nOutputs"] + r1["nPubInputs"]
+    state = {"nvars": r1["nVars"]}
+    gates, additions = [], []
+
+    def norm(lc):
+        return {s: v for s, v in lc.items() if v % r}
+
+    def lc_type(lc):                                                                 # :54-83
+        if any(s != 0 for s in lc):
+            return 2
+        return 1 if lc.get(0, 0) % r else 0
+
+    def join(lc1, lc2, k):                                                          # :94-115
+        res = {}
+        for s in sorted(lc1):
+            res[s] = (res.get(s, 0) + k * lc1[s]) % r
+        for s in sorted(lc2):
+            res[s] = (res.get(s, 0) - lc2[s]) % r
+        return norm(res)
+
+    def reduce_coefs(lc, max_c):                                                    # :117-160
+        k = 0
+        cs = []
+        for s in sorted(lc):
+            if s == 0:
+                k = (k + lc[s]) % r
+            else:
+                cs.append([s, lc[s]])
+        while len(cs) > max_c:
+            c1, c2 = cs.pop(0), cs.pop(0)
+            so = state["nvars"]
+            state["nvars"] += 1
+            gates.append((c1[0], c2[0], so, (-c1[1]) % r, (-c2[1]) % r, 0, 1, 0))
+            additions.append((c1[0], c2[0], c1[1], c2[1]))
+            cs.append([so, 1])
+        return k, [c[0] for c in cs] + [0] * (max_c - len(cs)), [c[1] for c in cs] + [0] * (max_c - len(cs))
+
+    for s in range(1, n_pub + 1):                                                   # getFFlonkConstantConstraint
+        gates.append((s, 0, 0, 1, 0, 0, 0, 0))
+    for la, lb, lc in r1["constraints"]:
+        la, lb, lc = (norm({int(s): int(v) % r for s, v in t}) for t in (la, lb, lc))
+        ta, tb = lc_type(la), lc_type(lb)
+        if ta == 0 or tb == 0:
+            lin = lc
+        elif ta == 1:
+            lin = join(lb, lc, la[0])
+        elif tb == 1:
+            lin = join(la, lc, lb[0])
+        else:
+            lin = None
+        if lin is not None:                                                         # processR1csAdditionConstraint :162-176
+            k, ss, cf = reduce_coefs(lin, 3)
+            gates.append((ss[0], ss[1], ss[2], cf[0], cf[1], 0, cf[2], k))
+        else:                                                                       # processR1csMultiplicationConstraint :178-199
+            ka, sa, ca = reduce_coefs(la, 1)
+            kb, sb_, cb = reduce_coefs(lb, 1)
+            kc, sc, cc = reduce_coefs(lc, 1)
+            gates.append((sa[0], sb_[0], sc[0], ca[0] * kb % r, ka * cb[0] % r, ca[0] * cb[0] % r, (-cc[0]) % r, (ka * kb - kc) % r))
+    return gates, additions, state["nvars"], n_pub
+
+
+def fflonk_setup(r1cs, ptau) -> bytes:
+    """src/fflonk_setup.js:59-559 from an r1cs and a ptau: the zkey the reference writes, byte for byte (section order 1, 3..17,
+    2).  Pinned by tests/test_oracle_fflonk.py against test/fflonk/circuit.zkey."""
+    from .plonk import _mont_from_ints
+    r1 = orc.read_r1cs(r1cs)
+    pdata, psecs = orc.read_binfile(ptau, "ptau", 1)
+    ph = orc.read_ptau_header(pdata, psecs)
+    ci = orc.curve_from_q(ph["q"])
+    r = ci.r
+    if r1["prime"] != r:
+        raise ValueError("r1cs curve does not match powers of tau ceremony curve")
+    if 12 not in psecs:
+        raise ValueError("Powers of Tau is not well prepared. Section 12 missing.")
+    gates, additions, n_vars, n_public = fflonk_gates_from_r1cs(r1, r)
+    ng = len(gates)
+    power = max(3, (ng + 2 - 1).bit_length())                                       # :112
+    n = 1 << power
+    sG1, sG2 = 2 * ci.n8q, 4 * ci.n8q
+    p2, l2 = psecs[2][0]
+    if l2 < (9 * n + 18) * sG1:
+        raise ValueError("Powers of Tau is not big enough for this circuit size. Section 2 too small.")
+    pts = bytes(pdata[p2:p2 + (9 * n + 18) * sG1])
+    wn = _fr_w(ci, power)
+    k1 = 2
+    while pow(k1, n, r) == 1:
+        k1 += 1
+    k2 = k1 + 1
+    while pow(k2, n, r) == 1 or pow(k2 * pow(k1, -1, r) % r, n, r) == 1:
+        k2 += 1
+    w3 = pow(31624, 3648040478639879203707734290876212514758060733402672390616367364429301415936 // 3, r)
+    w4, w8 = _fr_w(ci, 2), _fr_w(ci, 3)
+    wr = pow(467799165886069610036046866799264026481344299079011762026774533774345988080, 1 << (28 - power), r)
+    secs = [(1, struct.pack("<I", 10)),
+            (3, b"".join(struct.pack("<II", a[0], a[1]) + ci.fr_to_mont(a[2]) + ci.fr_to_mont(a[3]) for a in additions))]
+    for pos in range(3):
+        secs.append((4 + pos, np.array([g[pos] for g in gates], dtype="<u4").tobytes()))
+
+    def p4(evals_mont: bytes):
+        coef = bytes(orc.fr_fft(ci.id, evals_mont, True))
+        return coef + bytes(orc.fr_fft(ci.id, coef + bytes(3 * n * 32), False)), coef
+
+    polys = {}
+    for sid, name, pos in ((7, "QL", 3), (8, "QR", 4), (9, "QM", 5), (10, "QO", 6), (11, "QC", 7)):
+        payload, polys[name] = p4(_mont_from_ints(ci, [g[pos] for g in gates] + [0] * (n - ng)))
+        secs.append((sid, payload))
+    sigma = [0] * (3 * n)                                                           # writeSigma :340-415
+    last: Dict[int, int] = {}
+    first: Dict[int, int] = {}
+    w = 1
+    for i in range(n):
+        for col in range(3):
+            p = col * n + i
+            v = w if col == 0 else (w * k1 % r if col == 1 else w * k2 % r)
+            if i >= n - 2:
+                sigma[p] = v
+                continue
+            s = gates[i][col] if i < ng else 0
+            if s not in last:
+                first[s] = p
+            else:
+                sigma[p] = last[s]
+            last[s] = v
+        w = w * wn % r
+    for s, p in first.items():
+        sigma[p] = last[s]
+    for col, name in enumerate(("S1", "S2", "S3")):
+        payload, polys[name] = p4(_mont_from_ints(ci, sigma[col * n:(col + 1) * n]))
+        secs.append((12 + col, payload))
+    secs.append((15, b"".join(p4(_mont_from_ints(ci, [1 if j == i else 0 for j in range(n)]))[0] for i in range(max(n_public, 1)))))
+    secs.append((16, pts))
+    rows = np.stack([np.frombuffer(polys[k], dtype=np.uint8).reshape(n, 32) for k in ("QL", "QR", "QO", "QM", "QC", "S1", "S2", "S3")], axis=1)
+    c0_bytes = rows.reshape(8 * n * 32).tobytes()                                   # writeC0 :441-464
+    secs.append((17, c0_bytes))
+    jac = orc.multiexp_affine(ci.id, 1, pts[:8 * n * sG1], bytes(orc.batch_convert(ci.fr, False, c0_bytes)))
+    hdr = struct.pack("<I", ci.n8q) + ci.q.to_bytes(ci.n8q, "little") + struct.pack("<I", 32) + r.to_bytes(32, "little")
+    hdr += struct.pack("<IIIII", n_vars, n_public, n, len(additions), ng)
+    for v in (k1, k2, w3, w4, w8, wr):
+        hdr += ci.fr_to_mont(v)
+    p3, _ = psecs[3][0]
+    hdr += bytes(pdata[p3 + sG2:p3 + 2 * sG2])                                      # X_2 (:498-500)
+    hdr += bytes(orc.g_to_affine(ci.id, 1, jac))[:sG1]
+    return orc.write_binfile("zkey", 1, secs + [(2, hdr)])

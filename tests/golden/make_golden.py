@@ -132,6 +132,9 @@ def plonk_setup_cases():
         out[f"{tag}_ptau2"] = u8(bytes(O.section(pdata, psecs, 2)[:(n + 6) * 64]))
         out[f"{tag}_ptau12"] = u8(bytes(O.section(pdata, psecs, 12)[(n - 1) * 64:(2 * n - 1) * 64]))
     out["ptau3"] = u8(bytes(O.section(pdata, psecs, 3)[:256]))
+    # fflonk setup (test/fflonk, domain 256): r1cs + the first 9n + 18 points of ptau section 2
+    out["ff256_r1cs"] = u8(open(f"{REF}/fflonk/circuit.r1cs", "rb").read())
+    out["ff256_ptau2"] = u8(bytes(O.section(pdata, psecs, 2)[:(9 * 256 + 18) * 64]))
     np.savez_compressed(os.path.join(HERE, "plonk_setup_cases.npz"), **out)
     print("plonk_setup_cases:", {k: v.size for k, v in out.items()})
 

@@ -60,3 +60,11 @@ def test_synthetic_setup_prove_verify(n_gates, n_pub):
     vk = fflonk.fflonk_vk(zkey)
     assert len(public) == n_pub and fflonk.fflonk_verify(vk, public, proof)
     assert not fflonk.fflonk_verify(vk, [str(int(public[0]) ^ 1)] + public[1:], proof)
+
+
+def test_fflonk_setup_reproduces_reference_zkey_byte_for_byte(golden, ref_case):
+    """oracle.fflonk.fflonk_setup (r1cs -> gates and additions through r1cs_constraint_processor.js, selectors, sigmas with the
+    two blinding rows, Lagrange, PTau, C0, header) gives exactly test/fflonk/circuit.zkey (593 092 bytes, 100 additions)."""
+    g = golden("plonk_setup_cases.npz")
+    ptau = orc.write_binfile("ptau", 1, [(1, bytes(g["ptau_header"])), (2, bytes(g["ff256_ptau2"])), (3, bytes(g["ptau3"])), (12, b"")])
+    assert fflonk.fflonk_setup(bytes(g["ff256_r1cs"]), ptau) == ref_case["zkey"]
