@@ -28,5 +28,5 @@ def test_groth16_structured_key_proof_verifies(name):
     finally:
         curve.terminate()
     want, wpub = orc.groth16_prove(zkey, wtns, r, s)
-    assert (proof, public) == (want, wpub)
+    assert proof == want and [int(p) for p in public] == [int(p) for p in wpub]
     assert orc.groth16_verify(orc.zkey_vk(zkey), [int(p) for p in public], proof)
