@@ -1,20 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — Groth16 proofs/s on the BASELINE.json workload (BN254, domain 2^20 synthetic chain circuit).
+"""bench.py — proofs/s on the BASELINE.json workload (Groth16, BN254, domain 2^20 synthetic chain circuit).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 20] [--impl reference]
+                    [--workload groth16|plonk|fflonk] [--curve bn128|bls12381]
 
 One step = one proof.  N = 1: the whole prover on one B200.  N > 1 (torchrun, one rank per GPU): every MSM is sharded
-by point range across the ranks (north star / SURVEY §8e), the ranks exchange their five un-normalised MSM partials
-with one NCCL all-gather (a few hundred bytes), rank 0 assembles the proof; the QAP/NTT part is replicated
-("NTT stays single-GPU") — strong scaling of one proof.
+by point range across the ranks (north star / SURVEY §8e) and the three A/B/C transform chains run on different ranks;
+the exchange steps run inside libsnarkb200.so over NCCL.  `value` is the sharded single-proof rate (strong scaling);
+`replicas` reports N independent provers beside it.
 
 JSON keys follow the task contract; extra keys: roofline (dominant kernel vs measured HBM peak), roofline_int (same
 kernel vs the calibrated integer-pipe peak — the bound that actually applies), cpu_baseline (the oracle's
-restated reference prover on the host cores), breakdown_ms.
+restated reference prover on the host cores, same key, full size), breakdown_ms (per kernel class, serialised proof),
+oracle_match (the timed workload's proof equals the CPU oracle's: committed hash and, at N = 1, a live comparison).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,10 +38,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 domain of the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--workload", default="groth16", choices=["groth16", "plonk", "fflonk"])
+    ap.add_argument("--curve", default="bn128", choices=["bn128", "bls12381"])
+    ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 domain of the CPU arm's sample (0 = the full workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--witness-like", action="store_true", help="witness distribution of real circuits (SURVEY 8d): 50%% zeros, 25%% ones, 25%% uniform")
-    ap.add_argument("--check-oracle", action="store_true", help="also prove the full workload with the CPU oracle and compare proof bytes (minutes)")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"], help="N > 1: which number is `value` (the other one is reported beside it)")
     return ap.parse_args()
 
 
@@ -84,53 +89,90 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------------ host cores
+def host_cores() -> int:
+    """Threads the CPU arm may use: the affinity mask, capped by a cgroup CPU quota if one is set.  torchrun exports
+    OMP_NUM_THREADS=1 to its children; the CPU arm ignores it (it is the arm's whole job to use the host)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def proof_hash(proof_obj) -> str:
+    """sha256 of the canonical JSON text of the proof object (proof.json text identical)."""
+    return hashlib.sha256(json.dumps(proof_obj, sort_keys=True, separators=(",", ":")).encode()).hexdigest()
+
+
+def golden_hash(workload: str, curve: str, L: int, witness_like: bool):
+    if workload != "groth16" or curve != "bn128" or witness_like:
+        return None
+    try:
+        tab = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_proof_hashes.json")))
+        return tab["groth16_bn128_chain_r5_s7"].get(str(L))
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_reference_run(log_n: int, steps: int, warmup: int):
+def oracle_groth16(log_n: int, steps: int, warmup: int, zkey: bytes | None = None, witness: np.ndarray | None = None):
     """Times the oracle's restatement of groth16_prove.js (reference algorithms: pTSizes Pippenger, radix-2 DIT NTT,
-    serial buildABC1) on the host cores.  The synthetic key for the sample is built with the oracle's own point
-    generator so this arm needs no GPU."""
+    serial buildABC1) on all host cores.  Without a zkey the key is built with the oracle's own point generator (same
+    points as sb_gen_points), so this arm needs no GPU and proves the very key the B200 arm proves."""
     from oracle import oracle as O
-    import struct
     from snarkjs_b200 import synth
     ci = O.CURVES[O.BN254]
-    n = 1 << log_n
-
-    def g(grp, seed, k):
-        return O.gen_points(O.BN254, grp, seed, k).tobytes()
-    hdr = struct.pack("<I", 32) + ci.q.to_bytes(32, "little") + struct.pack("<I", 32) + ci.r.to_bytes(32, "little") + struct.pack("<III", n, 1, n)
-    hdr += g(1, 11, 1) + g(1, 12, 1) + g(2, 13, 1) + g(2, 14, 1) + g(1, 15, 1) + g(2, 16, 1)
-    secs = [(1, struct.pack("<I", 1)), (2, hdr), (3, g(1, 20, 2)), (4, synth.chain_coeffs(ci.r, log_n)), (5, g(1, 1, n)), (6, g(1, 2, n)),
-            (7, g(2, 3, n)), (8, g(1, 4, n - 2)), (9, g(1, 5, n)), (10, bytes(68))]
-    zkey = O.write_binfile("zkey", 1, secs)
-    wt = synth.wtns_container(ci.r, synth.chain_witness(ci.r, log_n))
+    cores = host_cores()
+    O.lib().or_set_threads(cores)
+    if zkey is None:
+        zkey = synth.groth16_zkey_image(ci.q, ci.r, 32, log_n, lambda g, s, k: O.gen_points(O.BN254, g, s, k).tobytes())
+    if witness is None:
+        witness = synth.chain_witness(ci.r, log_n)
+    wt = synth.wtns_container(ci.r, witness)
     r, s = ci.fr_to_mont(5), ci.fr_to_mont(7)
-    cores = O.lib().or_num_threads()
-    for _ in range(max(0, min(warmup, 1))):
-        O.groth16_prove(zkey, wt, r, s, concurrency=cores)
+    proof = None
+    for _ in range(warmup):
+        proof, _ = O.groth16_prove(zkey, wt, r, s, concurrency=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.groth16_prove(zkey, wt, r, s, concurrency=cores)
-    dt = (time.perf_counter() - t0) / steps
-    return dt, cores
+        proof, _ = O.groth16_prove(zkey, wt, r, s, concurrency=cores)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, cores, proof
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    log_n = args.cpu_log_n or min(18, args.log_n)
+    if args.workload != "groth16":
+        import bench_plonk
+        return bench_plonk.run_reference(args)
+    L = args.cpu_log_n or args.log_n
     steps = max(1, min(args.steps, 2))
-    dt, cores = cpu_reference_run(log_n, steps, args.warmup)
-    scale = (1 << args.log_n) / (1 << log_n)
+    warm = 1 if args.warmup > 0 else 0
+    dt, cores, proof = oracle_groth16(L, steps, warm)
+    scale = (1 << args.log_n) / (1 << L)
     val = 1.0 / (dt * scale)
-    sample = f"oracle groth16_prove on the chain circuit at domain 2^{log_n} ({steps} proofs, {dt:.3f} s each), scaled x{scale:g} (linear in constraints) to domain 2^{args.log_n}"
-    line = {"metric": "groth16_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integers)",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{args.log_n}", "curve": "bn128"},
-            "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample},
+    sample = f"oracle groth16_prove (restated reference prover) on the chain circuit at domain 2^{L}: {steps} proofs after {warm} warm-up, {dt:.3f} s each, {cores} OpenMP threads"
+    if scale != 1:
+        sample += f", scaled x{scale:g} (linear in constraints) to domain 2^{args.log_n}"
+    ph = proof_hash(proof)
+    gold = golden_hash("groth16", "bn128", L, False)
+    line = {"metric": "groth16_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{args.log_n}", "curve": "bn128",
+                       "same_key_as_b200_arm": True},
+            "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample, "nproc": os.cpu_count()},
             "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "proof_sha256": ph, "oracle_match": (ph == gold) if gold else None}
     print(json.dumps(line))
 
 
@@ -153,15 +195,14 @@ def run_b200(args):
     L = args.log_n
     curve = snarkjs_b200.getCurveFromName("bn128", device=local)
     peak_modmul = curve.lib.sb_calibrate(curve.handle, 1) if rank == 0 else 0.0
+    peak_imad = curve.lib.sb_calibrate(curve.handle, 0) if rank == 0 else 0.0
     t0 = time.perf_counter()
     zkey = synth.synth_groth16_zkey(curve, L, seed=1)
     pk = groth16.ProvingKey(zkey, curve=curve, shard=rank, n_shards=world)
     t_setup = time.perf_counter() - t0
     wit_np = synth.chain_witness(curve.r, L)
     if args.witness_like:
-        wl = wit_np.reshape(-1, 32).copy(); kind = np.random.default_rng(7).integers(0, 4, wl.shape[0])
-        wl[kind < 2] = 0; wl[kind == 2] = 0; wl[kind == 2, 0] = 1; wl[0] = 0; wl[0, 0] = 1
-        wit_np = wl.reshape(-1)
+        wit_np = synth.witness_like(wit_np)
     wit = torch.from_numpy(wit_np.copy()).pin_memory()           # pinned host witness: the e2e input
     wptr = wit.data_ptr()
     nwit = wit.numel() // 32
@@ -193,11 +234,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(resident, steps):
+    def timed(fn, steps):
         sync()
         t = time.perf_counter()
         for _ in range(steps):
-            step(resident)
+            fn()
         sync()
         dt = time.perf_counter() - t
         if dist is not None:
@@ -210,12 +251,12 @@ def run_b200(args):
         step(False)
     l0 = curve.launch_count()
     with ClockSampler(local) as cs:
-        dt_e2e = timed(False, args.steps)
+        dt_e2e = timed(lambda: step(False), args.steps)
         proof_e2e = proof.copy()
         l1 = curve.launch_count()
         # per-stage breakdown of the last e2e step (CUDA events on the library's stream)
         brk = {"h2d_witness": curve.last_ms(1), "device_total": curve.last_ms(0)}
-        dt_res = timed(True, args.steps)
+        dt_res = timed(lambda: step(True), args.steps)
     clocks = cs.summary()
     # kernel-level numbers for the rooflines: one extra proof with every stream serialised (in the overlapped schedule
     # kernels share the SMs, so their event-bracketed durations are not per-kernel costs)
@@ -225,12 +266,17 @@ def run_b200(args):
     acc = {"g1_ms": lib.sb_last_stat(h, 0), "g2_ms": lib.sb_last_stat(h, 1), "g1_launches": lib.sb_last_stat(h, 2),
            "g2_launches": lib.sb_last_stat(h, 3), "g1_entries": lib.sb_last_stat(h, 4), "g2_entries": lib.sb_last_stat(h, 5)}
     brk["serialised_device_total"] = curve.last_ms(0)
+    try:
+        names = ["digits_sort", "accumulate_g1", "accumulate_g2", "fold", "bucket_reduce", "qap_rows", "ntt_passes", "join_abc"]
+        for i, nm in enumerate(names):
+            brk[nm] = lib.sb_last_stat(h, 8 + i)
+    except Exception:
+        pass
     lib.sb_set_tuning(2, 0)
     assert np.array_equal(proof, proof_e2e), "resident and e2e proofs differ"
 
     if rank != 0:
         return
-    n = 1 << L
     # dominant kernel: the bucket-accumulation kernel (G1: 10 Fq modmul per entry, XYZZ mixed add 8M+2S;
     # G2: 8 Fq2 mul + 2 Fq2 sqr = 28 Fq modmul per entry).  Algorithmic bytes per entry: 8 B sorted (key,val) +
     # one affine base (64 / 128 B), plus the bucket array written once.
@@ -261,6 +307,9 @@ def run_b200(args):
     ach_mod = (k_mod / k_launch) / (avg_ms * 1e-3) if avg_ms > 0 else 0.0
     all_mod = (g1_mod + g2_mod)
     all_ms = acc["g1_ms"] + acc["g2_ms"]
+    pobj = groth16.proof_to_object(curve, proof.tobytes())
+    ph = proof_hash(pobj)
+    gold = golden_hash("groth16", "bn128", L, args.witness_like)
     line = {
         "metric": "groth16_proofs_per_sec", "value": args.steps / dt_res, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dt_res / args.steps * 1e3, "higher_is_better": True,
@@ -278,35 +327,47 @@ def run_b200(args):
                      "note": "integer-pipe bound kernel: see roofline_int; HBM fraction is low by construction"},
         "roofline_int": {"bound": "int32 IMAD pipe (modmul-bound roofline, SURVEY 8d)", "kernel": name, "achieved": ach_mod / 1e9, "unit": "G Fq-modmul/s",
                          "peak": peak_modmul / 1e9, "frac": ach_mod / peak_modmul if peak_modmul > 0 else None,
-                         "peak_source": "sb_calibrate(1): four independent per-thread BN254 Fq Montgomery-multiply chains (IMAD.WIDE.U32.X issue-bound), measured on this GPU in this run", "all_accumulate_kernels_frac": (all_mod / (all_ms * 1e-3)) / peak_modmul if (all_ms > 0 and peak_modmul > 0) else None},
+                         "peak_source": "sb_calibrate(1): four independent per-thread BN254 Fq Montgomery-multiply chains (IMAD.WIDE.U32.X issue-bound), measured on this GPU in this run",
+                         "imad_wide_per_s": peak_imad, "imad_wide_per_clk_per_sm": (peak_imad / 148.0 / (clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
+                         "all_accumulate_kernels_frac": (all_mod / (all_ms * 1e-3)) / peak_modmul if (all_ms > 0 and peak_modmul > 0) else None},
         "breakdown_ms": brk, "accumulate": acc, "setup_s": t_setup,
-        "proof_sha256": __import__("hashlib").sha256(proof.tobytes()).hexdigest(),   # same inputs => same bytes at every N
+        "proof_sha256": ph,                      # same inputs => same bytes at every N
+        "oracle_match": (ph == gold) if gold else None,
+        "oracle_match_source": "tests/golden/bench_proof_hashes.json (CPU oracle proof of this key, made by tests/golden/make_bench_hashes.py)" if gold else "no committed oracle hash for this size",
     }
-    if not args.no_cpu_baseline:
-        try:
-            log_s = args.cpu_log_n or min(16, L)
-            dt, cores = cpu_reference_run(log_s, 1, 0)
-            scale = (1 << L) / (1 << log_s)
-            line["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": "proofs/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle (restated reference prover) on the chain circuit at domain 2^{log_s}: {dt:.3f} s, scaled x{scale:g} linearly to 2^{L}"}
+    if gold and ph != gold:
+        line["oracle_mismatch"] = {"got": ph, "want": gold}
+    if not args.no_cpu_baseline and world == 1:
+        try:   # the CPU oracle proves the SAME key and witness (full size unless --cpu-log-n): baseline + live parity check
+            Ls = args.cpu_log_n or L
+            if Ls == L:
+                dt, cores, oproof = oracle_groth16(L, 1, 0, zkey=zkey, witness=wit_np)
+                line["oracle_live_match"] = (oproof == pobj)
+                sample = f"oracle (restated reference prover) proving the same key and witness at domain 2^{L}: one proof, {dt:.3f} s, {cores} OpenMP threads"
+                val = 1.0 / dt
+            else:
+                dt, cores, _ = oracle_groth16(Ls, 1, 0)
+                scale = (1 << L) / (1 << Ls)
+                sample = f"oracle (restated reference prover) on the chain circuit at domain 2^{Ls}: {dt:.3f} s, {cores} OpenMP threads, scaled x{scale:g} linearly to 2^{L}"
+                val = 1.0 / (dt * scale)
+            line["cpu_baseline"] = {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample, "nproc": os.cpu_count()}
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"error": str(e)}
-    if args.check_oracle:
-        from oracle import oracle as O
-        ci = O.CURVES[O.BN254]
-        t0 = time.perf_counter()
-        oproof, _ = O.groth16_prove(zkey, synth.wtns_container(curve.r, wit_np), r, s, concurrency=O.lib().or_num_threads())
-        line["oracle_check"] = {"match": groth16.proof_to_object(curve, proof.tobytes()) == oproof, "oracle_seconds": time.perf_counter() - t0}
     print(json.dumps(line))
     pk.release()
     curve.terminate()
     if dist is not None:
         dist.destroy_process_group()
+    if gold and ph != gold:
+        sys.exit("proof does not match the CPU oracle's (tests/golden/bench_proof_hashes.json)")
 
 
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload != "groth16":
+        import bench_plonk
+        bench_plonk.run_b200(a)
     else:
         run_b200(a)

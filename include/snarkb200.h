@@ -14,8 +14,10 @@
  *   - return 0 on success, negative on error; sb_last_error(ctx) gives the message — the JS shim throws
  *     `new Error(msg)` so that error strings match the reference's;
  *   - the callee never retains caller memory (reference: inputs are sliced/copied, 14645-14646, 14739);
- *   - a context is bound to one CUDA device; calls on one context are serialised by the caller
- *     (one context per thread / per GPU).
+ *   - a context is bound to one CUDA device.  Every call locks its context for its duration, so overlapping calls on
+ *     one context from several threads are safe and run one after the other (the reference awaits several bulk calls at
+ *     once, 14653 / 14929-14932; an N-API shim runs them as AsyncWorkers on libuv threads).  For concurrency use one
+ *     context per thread / per GPU.  sb_last_error returns the message of the calling thread's last failed call.
  */
 #ifndef SNARKB200_H
 #define SNARKB200_H
@@ -170,7 +172,8 @@ double sb_last_stat(sb_ctx* ctx, int which);
 double sb_calibrate(sb_ctx* ctx, int what);
 /* experimental kernel-variant selection (process-wide): key 0 = bucket-accumulation minBlocksPerSM variant. */
 int sb_set_tuning(int key, int value);
-/* synthetic bases for tests/benchmarks: P_i = (SplitMix64(seed+i)|1) * G, affine Montgomery, computed on the GPU. */
+/* synthetic bases for tests/benchmarks: chunks of 4096 points P_{c,j} = (k0(seed, c) + j*kd(seed)) * G, affine Montgomery, computed
+ * on the GPU; the same points as the CPU oracle's incremental generator (oracle/snark_oracle.cpp or_gen_points), see msm.cuh. */
 int sb_gen_points(sb_ctx* ctx, int group, uint64_t seed, uint64_t n, uint8_t* out);
 int sb_generator(sb_ctx* ctx, int group, uint8_t* out_affine);
 int sb_sync(sb_ctx* ctx);

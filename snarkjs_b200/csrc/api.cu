@@ -64,6 +64,7 @@ struct Groth16Key {
     int shard = 0, n_shards = 1; uint64_t wlo = 0, wcnt = 0, hlo = 0, hcnt = 0;
     uint64_t* d_rowptr = nullptr; uint32_t* d_sig = nullptr; void* d_coef = nullptr; uint64_t nCoef = 0;
     // device work buffers
+    bool witness_resident = false;   // set by the first upload: sb_groth16_prove_resident refuses to run before it
     void *dW = nullptr, *dA_T = nullptr, *dB_T = nullptr, *dC_T = nullptr, *dTmp = nullptr, *dTmp2 = nullptr, *dTmp3 = nullptr, *dWsum = nullptr;
 };
 
@@ -75,6 +76,11 @@ namespace { struct FflonkKeyDev; void fflonk_free_key(FflonkKeyDev*); }  // api_
 static constexpr size_t STAGE_BYTES = 8u << 20;
 
 struct sb_ctx {
+    // Every entry point that takes a context locks it for the duration of the call: overlapping calls on one context
+    // (the reference awaits several bulk calls at once, build/snarkjs.js:14653, 14929-14932; the N-API shim runs them
+    // as AsyncWorkers on libuv threads) are serialised here instead of racing on the staging buffers and streams.
+    // Recursive because some entries are thin wrappers over others (prove_wtns -> prove, load_file -> load).
+    std::recursive_mutex mu;
     int curve = 0, device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -110,7 +116,12 @@ struct sb_ctx {
 
 namespace {
 
-int fail(sb_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+// the message of the last failed call is kept per calling thread, so that two threads sharing a context each read
+// their own error text from sb_last_error
+thread_local const sb_ctx* t_err_ctx = nullptr;
+thread_local std::string t_err;
+int fail(sb_ctx* c, int code, const std::string& msg) { if (c) { c->err = msg; t_err_ctx = c; t_err = msg; } return code; }
+#define SB_LOCK(c) std::unique_lock<std::recursive_mutex> _sb_lk; if (c) _sb_lk = std::unique_lock<std::recursive_mutex>((c)->mu)
 int cuda_fail(sb_ctx* c, cudaError_t e, const char* where) {
     return fail(c, e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
@@ -427,9 +438,9 @@ int parse_binfile(sb_ctx* c, const uint8_t* d, uint64_t len, const char* magic, 
     if (ver > max_version) return fail(c, SB_ERR_FORMAT, "Version not supported");
     uint64_t pos = 12;
     for (uint32_t i = 0; i < nsec; i++) {
-        if (pos + 12 > len) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        if (len - pos < 12) return fail(c, SB_ERR_FORMAT, "Invalid file size");
         uint32_t id; uint64_t sl; memcpy(&id, d + pos, 4); memcpy(&sl, d + pos + 4, 8); pos += 12;
-        if (pos + sl > len) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        if (sl > len - pos) return fail(c, SB_ERR_FORMAT, "Invalid file size");   // (not pos + sl > len: sl comes from the file and may wrap)
         if (secs[id].present) return fail(c, SB_ERR_FORMAT, "Section Duplicated " + std::to_string(id));
         secs[id].pos = pos; secs[id].len = sl; secs[id].present = true;
         pos += sl;
@@ -516,19 +527,23 @@ void sb_destroy(sb_ctx* c) {
     delete c;
 }
 
-const char* sb_last_error(sb_ctx* c) { return c ? c->err.c_str() : "null context"; }
-uint64_t sb_launch_count(sb_ctx* c) { return c ? c->launches + (uint64_t)c->stats.launches : 0; }
-float sb_last_ms(sb_ctx* c, int which) { return (c && which >= 0 && which < 8) ? c->last_ms[which] : 0.f; }
-int sb_sync(sb_ctx* c) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+const char* sb_last_error(sb_ctx* c) {
+    if (!c) return "null context";
+    if (t_err_ctx == c) return t_err.c_str();
+    SB_LOCK(c); t_err_ctx = c; t_err = c->err; return t_err.c_str();
+}
+uint64_t sb_launch_count(sb_ctx* c) { SB_LOCK(c); return c ? c->launches + (uint64_t)c->stats.launches : 0; }
+float sb_last_ms(sb_ctx* c, int which) { SB_LOCK(c); return (c && which >= 0 && which < 8) ? c->last_ms[which] : 0.f; }
+int sb_sync(sb_ctx* c) { SB_LOCK(c); if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
 
-int sb_msm_g1_affine(sb_ctx* c, const uint8_t* bases, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
+int sb_msm_g1_affine(sb_ctx* c, const uint8_t* bases, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) { SB_LOCK(c);
     return msm_host_inputs(c, SB_G1, bases, nullptr, scalars, sb, n, out, nullptr);
 }
-int sb_msm_g2_affine(sb_ctx* c, const uint8_t* bases, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
+int sb_msm_g2_affine(sb_ctx* c, const uint8_t* bases, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) { SB_LOCK(c);
     return msm_host_inputs(c, SB_G2, bases, nullptr, scalars, sb, n, out, nullptr);
 }
 
-int sb_bases_register(sb_ctx* c, int group, const uint8_t* bases, uint64_t n, uint64_t* handle) {
+int sb_bases_register(sb_ctx* c, int group, const uint8_t* bases, uint64_t n, uint64_t* handle) { SB_LOCK(c);
     if (!c || !handle || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
@@ -540,7 +555,7 @@ int sb_bases_register(sb_ctx* c, int group, const uint8_t* bases, uint64_t n, ui
     *handle = c->bases.size();
     return 0;
 }
-int sb_bases_release(sb_ctx* c, uint64_t h) {
+int sb_bases_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
     if (!c || h == 0 || h > c->bases.size() || !c->bases[h - 1].d) return fail(c, SB_ERR_ARG, "invalid bases handle");
     cudaSetDevice(c->device);
     cudaFree(c->bases[h - 1].d); c->bases[h - 1].d = nullptr; c->bases[h - 1].n = 0;
@@ -556,14 +571,14 @@ static int msm_registered_impl(sb_ctx* c, uint64_t h, uint64_t first, const uint
         return msm_host_inputs(c, b.group, nullptr, b.table, scalars, sb, n, out, partial, &b.gp, first);
     return msm_host_inputs(c, b.group, nullptr, (const uint8_t*)b.d + first * G.aff_bytes, scalars, sb, n, out, partial);
 }
-int sb_msm_registered(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) {
+int sb_msm_registered(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* out) { SB_LOCK(c);
     return msm_registered_impl(c, h, first, scalars, sb, n, out, nullptr);
 }
-int sb_msm_registered_partial(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* partial) {
+int sb_msm_registered_partial(sb_ctx* c, uint64_t h, uint64_t first, const uint8_t* scalars, uint32_t sb, uint64_t n, uint8_t* partial) { SB_LOCK(c);
     return msm_registered_impl(c, h, first, scalars, sb, n, nullptr, partial);
 }
 uint32_t sb_msm_partial_bytes(sb_ctx* c, int group) { return c ? (group == SB_G1 ? c->g1.xyzz_bytes : c->g2.xyzz_bytes) : 0; }
-int sb_msm_sum_partials(sb_ctx* c, int group, const uint8_t* partials, int count, uint8_t* out) {
+int sb_msm_sum_partials(sb_ctx* c, int group, const uint8_t* partials, int count, uint8_t* out) { SB_LOCK(c);
     if (!c || (group != SB_G1 && group != SB_G2) || count < 0) return SB_ERR_ARG;
     const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
     std::vector<uint8_t> acc(G.xyzz_bytes, 0);
@@ -572,7 +587,7 @@ int sb_msm_sum_partials(sb_ctx* c, int group, const uint8_t* partials, int count
     return 0;
 }
 
-int sb_msm_dev(sb_ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint32_t sb, uint64_t n, uint8_t* out) {
+int sb_msm_dev(sb_ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint32_t sb, uint64_t n, uint8_t* out) { SB_LOCK(c);
     if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
@@ -603,7 +618,7 @@ static int ntt_dev(sb_ctx* c, void* a, void* b, uint64_t n, int inverse, const F
     return 0;
 }
 
-int sb_ntt_fr(sb_ctx* c, const uint8_t* in, uint64_t n, int inverse, uint8_t* out) {
+int sb_ntt_fr(sb_ctx* c, const uint8_t* in, uint64_t n, int inverse, uint8_t* out) { SB_LOCK(c);
     if (!c) return SB_ERR_ARG;
     if (n == 0 || (n & (n - 1))) return fail(c, SB_ERR_ARG, "fft must be multiple of 2");
     cudaSetDevice(c->device);
@@ -621,7 +636,7 @@ int sb_ntt_fr(sb_ctx* c, const uint8_t* in, uint64_t n, int inverse, uint8_t* ou
     c->last_ms[0] = elapsed(c, 0, 3); c->last_ms[1] = elapsed(c, 0, 1); c->last_ms[2] = elapsed(c, 1, 2); c->last_ms[3] = elapsed(c, 2, 3);
     return 0;
 }
-int sb_ntt_fr_dev(sb_ctx* c, void* data, void* scratch, uint64_t n, int inverse, void** result) {
+int sb_ntt_fr_dev(sb_ctx* c, void* data, void* scratch, uint64_t n, int inverse, void** result) { SB_LOCK(c);
     if (!c || !result) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     tick(c, 0);
@@ -632,7 +647,7 @@ int sb_ntt_fr_dev(sb_ctx* c, void* data, void* scratch, uint64_t n, int inverse,
     return 0;
 }
 
-int sb_fr_batch_apply_key(sb_ctx* c, const uint8_t* in, uint64_t n, const uint8_t first[32], const uint8_t inc[32], uint8_t* out) {
+int sb_fr_batch_apply_key(sb_ctx* c, const uint8_t* in, uint64_t n, const uint8_t first[32], const uint8_t inc[32], uint8_t* out) { SB_LOCK(c);
     if (!c) return SB_ERR_ARG;
     if (n == 0) return 0;
     cudaSetDevice(c->device);
@@ -657,10 +672,10 @@ static int convert_impl(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, 
     CU(c, d2h(c, out, b, n * 32));
     return 0;
 }
-int sb_fr_batch_to_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { return convert_impl(c, in, n, out, 1); }
-int sb_fr_batch_from_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { return convert_impl(c, in, n, out, 0); }
+int sb_fr_batch_to_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { SB_LOCK(c); return convert_impl(c, in, n, out, 1); }
+int sb_fr_batch_from_montgomery(sb_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out) { SB_LOCK(c); return convert_impl(c, in, n, out, 0); }
 
-int sb_qap_join_abc(sb_ctx* c, const uint8_t* a, const uint8_t* b, const uint8_t* cc, uint64_t n, uint8_t* out) {
+int sb_qap_join_abc(sb_ctx* c, const uint8_t* a, const uint8_t* b, const uint8_t* cc, uint64_t n, uint8_t* out) { SB_LOCK(c);
     if (!c) return SB_ERR_ARG;
     if (n == 0) return 0;
     cudaSetDevice(c->device);
@@ -675,7 +690,7 @@ int sb_qap_join_abc(sb_ctx* c, const uint8_t* a, const uint8_t* b, const uint8_t
     return 0;
 }
 
-int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) {
+int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) { SB_LOCK(c);
     if (!c) return SB_ERR_ARG;
     if (what == -1) memcpy(out, c->shift.data(), 32);
     else if (what == -2) memcpy(out, c->nqr.data(), 32);
@@ -689,9 +704,9 @@ int sb_set_tuning(int key, int value) {
     if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
     if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
 }
-double sb_last_stat(sb_ctx* c, int which) { return (c && which >= 0 && which < 8) ? c->stat[which] : 0.0; }
-double sb_calibrate(sb_ctx* c, int what) { if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
-int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out) {
+double sb_last_stat(sb_ctx* c, int which) { SB_LOCK(c); return (c && which >= 0 && which < 8) ? c->stat[which] : 0.0; }
+double sb_calibrate(sb_ctx* c, int what) { SB_LOCK(c); if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
+int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out) { SB_LOCK(c);
     if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     const GroupOps& G = group == SB_G1 ? c->g1 : c->g2;
@@ -702,16 +717,16 @@ int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out)
     CU(c, d2h(c, out, d, n * G.aff_bytes));
     return 0;
 }
-int sb_generator(sb_ctx* c, int group, uint8_t* out) {
+int sb_generator(sb_ctx* c, int group, uint8_t* out) { SB_LOCK(c);
     if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
     const std::vector<uint8_t>& g = group == SB_G1 ? c->gen1 : c->gen2;
     memcpy(out, g.data(), g.size()); return 0;
 }
 
-void* sb_dev_alloc(sb_ctx* c, uint64_t bytes) { if (!c) return nullptr; cudaSetDevice(c->device); void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; return p; }
-int sb_dev_free(sb_ctx* c, void* p) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaFree(p)); return 0; }
-int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, h2d(c, dst, src, bytes)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
-int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, d2h(c, dst, src, bytes)); return 0; }
+void* sb_dev_alloc(sb_ctx* c, uint64_t bytes) { SB_LOCK(c); if (!c) return nullptr; cudaSetDevice(c->device); void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; return p; }
+int sb_dev_free(sb_ctx* c, void* p) { SB_LOCK(c); if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, cudaFree(p)); return 0; }
+int sb_dev_upload(sb_ctx* c, void* dst, const uint8_t* src, uint64_t bytes) { SB_LOCK(c); if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, h2d(c, dst, src, bytes)); CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+int sb_dev_download(sb_ctx* c, uint8_t* dst, const void* src, uint64_t bytes) { SB_LOCK(c); if (!c) return SB_ERR_ARG; cudaSetDevice(c->device); CU(c, d2h(c, dst, src, bytes)); return 0; }
 
 // ---------------------------------------------------------------------------------------------------- Groth16
 // A zkey comes either as a memory image (z != nullptr) or as a file streamed section by section: the small sections
@@ -734,7 +749,7 @@ static int zkey_section_table(sb_ctx* c, ZkeySource& src, std::map<uint32_t, Sec
     for (uint32_t i = 0; i < nsec; i++) {
         if (fseek(src.f, (long)pos, SEEK_SET) || fread(hd, 1, 12, src.f) != 12) return fail(c, SB_ERR_FORMAT, "Invalid file size");
         uint32_t id; uint64_t sl; memcpy(&id, hd, 4); memcpy(&sl, hd + 4, 8); pos += 12;
-        if (pos + sl > flen) return fail(c, SB_ERR_FORMAT, "Invalid file size");
+        if (pos > flen || sl > flen - pos) return fail(c, SB_ERR_FORMAT, "Invalid file size");
         if (secs[id].present) return fail(c, SB_ERR_FORMAT, "Section Duplicated " + std::to_string(id));
         secs[id].pos = pos; secs[id].len = sl; secs[id].present = true; pos += sl;
     }
@@ -877,16 +892,16 @@ static int groth16_load_impl(sb_ctx* c, ZkeySource& src, int shard, int n_shards
     return 0;
 }
 
-int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) {
+int sb_groth16_load(sb_ctx* c, const uint8_t* z, uint64_t zlen, uint64_t* handle) { SB_LOCK(c);
     if (!z) return SB_ERR_ARG;
     ZkeySource src; src.z = z; src.zlen = zlen; return groth16_load_impl(c, src, 0, 1, handle);
 }
-int sb_groth16_load_sharded(sb_ctx* c, const uint8_t* z, uint64_t zlen, int shard, int n_shards, uint64_t* handle) {
+int sb_groth16_load_sharded(sb_ctx* c, const uint8_t* z, uint64_t zlen, int shard, int n_shards, uint64_t* handle) { SB_LOCK(c);
     if (!z) return SB_ERR_ARG;
     ZkeySource src; src.z = z; src.zlen = zlen; return groth16_load_impl(c, src, shard, n_shards, handle);
 }
 
-int sb_groth16_load_file(sb_ctx* c, const char* path, uint64_t* handle) {
+int sb_groth16_load_file(sb_ctx* c, const char* path, uint64_t* handle) { SB_LOCK(c);
     if (!c || !path) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     FILE* f = fopen(path, "rb");
@@ -899,12 +914,12 @@ int sb_groth16_load_file(sb_ctx* c, const char* path, uint64_t* handle) {
 
 static Groth16Key* get_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->keys.size()) ? c->keys[h - 1] : nullptr; }
 
-int sb_groth16_info(sb_ctx* c, uint64_t h, uint32_t* nv, uint32_t* np, uint32_t* ds) {
+int sb_groth16_info(sb_ctx* c, uint64_t h, uint32_t* nv, uint32_t* np, uint32_t* ds) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     if (nv) *nv = k->nVars; if (np) *np = k->nPublic; if (ds) *ds = k->domainSize;
     return 0;
 }
-int sb_groth16_release(sb_ctx* c, uint64_t h) {
+int sb_groth16_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     cudaSetDevice(c->device); free_key(k); c->keys[h - 1] = nullptr; return 0;
 }
@@ -918,7 +933,8 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
     const int cv = c->curve;
     int rc;
     tick(c, 0);
-    if (witness) CU(c, h2d(c, k->dW, witness, nv * 32));
+    if (witness) { k->witness_resident = false; CU(c, h2d(c, k->dW, witness, nv * 32)); k->witness_resident = true; }
+    else if (!k->witness_resident) return fail(c, SB_ERR_ARG, "no witness resident for this proving key: call sb_groth16_prove first");
     tick(c, 1);
     prof_begin(c);
     void* tmp = k->dTmp;
@@ -1117,25 +1133,25 @@ static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& 
     return 0;
 }
 
-int sb_groth16_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+int sb_groth16_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     if (k->n_shards > 1) return fail(c, SB_ERR_ARG, "proving key was loaded sharded: use sb_groth16_prove_shard + sb_groth16_finish");
     std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
     int rc = groth16_device(c, k, witness, n_witness, 0, 1, partials.data()); if (rc) return rc;
     return groth16_assemble(c, k, partials.data(), r, s, proof);
 }
-int sb_groth16_prove_resident(sb_ctx* c, uint64_t h, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+int sb_groth16_prove_resident(sb_ctx* c, uint64_t h, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
     int rc = groth16_device(c, k, nullptr, k->nVars, 0, 1, partials.data()); if (rc) return rc;
     return groth16_assemble(c, k, partials.data(), r, s, proof);
 }
-int sb_groth16_prove_shard(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials_out) {
+int sb_groth16_prove_shard(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials_out) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(c, SB_ERR_ARG, "invalid shard");
     return groth16_device(c, k, witness, n_witness, shard, n_shards, partials_out);
 }
-int sb_groth16_finish(sb_ctx* c, uint64_t h, const uint8_t* all, int n_shards, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+int sb_groth16_finish(sb_ctx* c, uint64_t h, const uint8_t* all, int n_shards, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
     const uint32_t x1 = G1.xyzz_bytes, pb = sb_groth16_partials_bytes(c);
@@ -1193,12 +1209,13 @@ void sb_shard_range(uint64_t total, int shard, int n_shards, uint64_t* first, ui
     *first = lo; *count = std::min(total - lo, per);
 }
 
-int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     std::map<uint32_t, Section> secs;
     int rc = parse_binfile(c, w, wlen, "wtns", 2, secs); if (rc) return rc;
     if (!secs[1].present || !secs[2].present) return fail(c, SB_ERR_FORMAT, "Missing section");
     const uint8_t* hd = w + secs[1].pos;
+    if (secs[1].len < 4) return fail(c, SB_ERR_FORMAT, "wtns header too short");
     uint32_t n8; memcpy(&n8, hd, 4);
     if (secs[1].len < 8 + (uint64_t)n8) return fail(c, SB_ERR_FORMAT, "wtns header too short");
     if (!modulus_matches(hd + 4, n8, c->curve, true)) return fail(c, SB_ERR_ARG, "Curve of the witness does not match the curve of the proving key");
@@ -1216,7 +1233,7 @@ int sb_groth16_prove_wtns(sb_ctx* c, uint64_t h, const uint8_t* w, uint64_t wlen
 
 extern "C" {
 
-int sb_plonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle) {
+int sb_plonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle) { SB_LOCK(c);
     if (!c || !zkey || !handle) return SB_ERR_ARG;
     cudaSetDevice(c->device);
     return c->curve == SB_BN254 ? plonk_load_impl<BnFr>(c, zkey, len, handle) : plonk_load_impl<BlsFr>(c, zkey, len, handle);
@@ -1237,22 +1254,22 @@ static int load_mapped(sb_ctx* c, const char* path, uint64_t* handle, int (*load
     munmap(p, (size_t)st.st_size);
     return rc;
 }
-int sb_plonk_load_file(sb_ctx* c, const char* path, uint64_t* handle) { return load_mapped(c, path, handle, sb_plonk_load); }
+int sb_plonk_load_file(sb_ctx* c, const char* path, uint64_t* handle) { SB_LOCK(c); return load_mapped(c, path, handle, sb_plonk_load); }
 static PlonkKeyDev* get_plonk_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->plonk_keys.size()) ? c->plonk_keys[h - 1] : nullptr; }
-int sb_plonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) {
+int sb_plonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) { SB_LOCK(c);
     PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
     if (n_vars) *n_vars = k->z.nVars; if (n_public) *n_public = k->z.nPublic; if (domain_size) *domain_size = k->z.n; if (n_additions) *n_additions = k->z.nAdditions;
     return 0;
 }
 uint32_t sb_plonk_proof_bytes(sb_ctx* c) { return c ? 9 * c->g1.aff_bytes + 6 * 32 : 0; }
-int sb_plonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders, uint8_t* proof) {
+int sb_plonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders, uint8_t* proof) { SB_LOCK(c);
     PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
     if (!witness || !blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
     cudaSetDevice(c->device);
     return c->curve == SB_BN254 ? plonk_prove_impl<BnFq, BnFr>(c, k, witness, n_witness, blinders, proof)
                                 : plonk_prove_impl<BlsFq, BlsFr>(c, k, witness, n_witness, blinders, proof);
 }
-int sb_plonk_release(sb_ctx* c, uint64_t h) {
+int sb_plonk_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
     PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
     plonk_free_key(k); c->plonk_keys[h - 1] = nullptr;
@@ -1260,27 +1277,27 @@ int sb_plonk_release(sb_ctx* c, uint64_t h) {
 }
 
 // ---- fflonk (src/fflonk_prove.js)
-int sb_fflonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle) {
+int sb_fflonk_load(sb_ctx* c, const uint8_t* zkey, uint64_t len, uint64_t* handle) { SB_LOCK(c);
     if (!c || !zkey || !handle) return SB_ERR_ARG;
     if (c->curve != SB_BN254) return fail(c, SB_ERR_ARG, "fflonk is defined on bn128 only (src/fflonk_setup.js:534-557)");
     cudaSetDevice(c->device);
     return fflonk_load_impl<BnFr>(c, zkey, len, handle);
 }
-int sb_fflonk_load_file(sb_ctx* c, const char* path, uint64_t* handle) { return load_mapped(c, path, handle, sb_fflonk_load); }
+int sb_fflonk_load_file(sb_ctx* c, const char* path, uint64_t* handle) { SB_LOCK(c); return load_mapped(c, path, handle, sb_fflonk_load); }
 static FflonkKeyDev* get_fflonk_key(sb_ctx* c, uint64_t h) { return (c && h >= 1 && h <= c->fflonk_keys.size()) ? c->fflonk_keys[h - 1] : nullptr; }
-int sb_fflonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) {
+int sb_fflonk_info(sb_ctx* c, uint64_t h, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions) { SB_LOCK(c);
     FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
     if (n_vars) *n_vars = k->z.nVars; if (n_public) *n_public = k->z.nPublic; if (domain_size) *domain_size = k->z.n; if (n_additions) *n_additions = k->z.nAdditions;
     return 0;
 }
 uint32_t sb_fflonk_proof_bytes(sb_ctx* c) { return c ? 4 * c->g1.aff_bytes + 16 * 32 : 0; }
-int sb_fflonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders, uint8_t* proof) {
+int sb_fflonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders, uint8_t* proof) { SB_LOCK(c);
     FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
     if (!witness || !blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
     cudaSetDevice(c->device);
     return fflonk_prove_impl<BnFq, BnFr>(c, k, witness, n_witness, blinders, proof);
 }
-int sb_fflonk_release(sb_ctx* c, uint64_t h) {
+int sb_fflonk_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
     FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
     fflonk_free_key(k); c->fflonk_keys[h - 1] = nullptr;

@@ -357,22 +357,30 @@ __global__ void __launch_bounds__(128) k_precompute(const Affine<F>* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Synthetic bases for benchmarks and tests: P_i = k_i * G with k_i = SplitMix64(seed + i) (64-bit), written
-// as affine Montgomery points.  One thread per point: double-and-add in XYZZ, then one field inversion.
-// ------------------------------------------------------------------------------------------------
+// Synthetic bases for benchmarks and tests, written as affine Montgomery points.  The definition is the CPU
+// oracle's incremental generator (chunks of 4096 points: P_{c,0} = k0(c)*G, P_{c,j+1} = P_{c,j} + kd*G), which costs the
+// host two additions per point; here every point is computed independently as (k0(c) + j*kd)*G — the same group
+// element, hence the same affine bytes — so the B200 arm and the CPU reference arm of bench.py build identical keys.
+// One thread per point: 77-bit double-and-add in XYZZ, then one field inversion.
 __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
 }
+static constexpr uint64_t GEN_CHUNK = 4096;
 template <class F>
 __global__ void __launch_bounds__(128) k_gen_points(Affine<F> g, uint64_t seed, uint64_t n, Affine<F>* __restrict__ out) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = splitmix64(seed + i) | 1ull;
+    const uint64_t c = i / GEN_CHUNK, j = i % GEN_CHUNK;
+    const uint64_t k0 = (seed ^ 0x9E3779B97F4A7C15ull) + c * 0xD1B54A32D192ED03ull, kd = seed * 2654435761ull + 12345ull;
+    // s = k0 + j*kd  (< 2^77) as (hi, lo)
+    uint64_t lo = j * kd, hi = __umul64hi(j, kd);
+    lo += k0; hi += lo < k0 ? 1 : 0;
     const F one = F::one();
     XYZZ<F> r = XYZZ<F>::inf();
-    for (int bit = 63; bit >= 0; bit--) {
+    for (int bit = 79; bit >= 0; bit--) {
         r = XYZZ<F>::dbl(r);
-        if ((k >> bit) & 1) r.add_affine(g.x, g.y, one);
+        const uint64_t wd = bit >= 64 ? hi : lo;
+        if ((wd >> (bit & 63)) & 1) r.add_affine(g.x, g.y, one);
     }
     Affine<F> a;
     if (r.is_inf()) { a.x = F::zero(); a.y = F::zero(); }

@@ -1,52 +1,4 @@
-// MSM instantiation: bn254_g2 (coordinate field Fp2<BnFq>)
-#include "msm_host.cuh"
-#include "msm_entry.h"
-namespace sb {
-typedef Fp2<BnFq> FT;
-typedef XYZZ<FT> PT;
-int bn254_g2_buckets(const void* d_bases, const MsmSorted& s, MsmScratch& scratch, cudaStream_t stream, void* d_wsum, MsmLaunchStats* stats,
-                   cudaStream_t tail_stream, cudaEvent_t ev_acc) {
-    return msm_buckets<FT>((const Affine<FT>*)d_bases, s, scratch, stream, (PT*)d_wsum, stats, tail_stream, ev_acc);
-}
-void bn254_g2_combine(const uint8_t* wsum_host, const MsmGeom& g, uint8_t* acc_xyzz) {
-    PT acc; memcpy(&acc, acc_xyzz, sizeof acc);
-    if (g.precomp) { PT r; memcpy(&r, wsum_host, sizeof r); acc.add(r); }   // single shared bucket set: no Horner
-    else {
-        std::vector<PT> ws(g.W); memcpy(ws.data(), wsum_host, (size_t)g.W * sizeof(PT));
-        msm_combine_host<FT>(ws.data(), g, acc);
-    }
-    memcpy(acc_xyzz, &acc, sizeof acc);
-}
-void bn254_g2_add(uint8_t* acc_xyzz, const uint8_t* other_xyzz) {
-    PT a, b; memcpy(&a, acc_xyzz, sizeof a); memcpy(&b, other_xyzz, sizeof b); a.add(b); memcpy(acc_xyzz, &a, sizeof a);
-}
-void bn254_g2_to_jacobian(const uint8_t* xyzz, uint8_t* out) { PT p; memcpy(&p, xyzz, sizeof p); xyzz_to_jacobian_bytes<FT>(p, out); }
-void bn254_g2_to_affine(const uint8_t* xyzz, uint8_t* out) {
-    PT p; memcpy(&p, xyzz, sizeof p);
-    if (p.is_inf()) { memset(out, 0, 2 * sizeof(FT)); return; }
-    FT x = FT::mul(p.x, FT::inv(p.zz)), y = FT::mul(p.y, FT::inv(p.zzz));
-    memcpy(out, &x, sizeof x); memcpy(out + sizeof x, &y, sizeof y);
-}
-void bn254_g2_from_affine(const uint8_t* aff, uint8_t* xyzz) {
-    Affine<FT> a; memcpy(&a, aff, sizeof a);
-    PT p = PT::inf();
-    if (!a.is_inf()) { p.x = a.x; p.y = a.y; p.zz = FT::one(); p.zzz = FT::one(); }
-    memcpy(xyzz, &p, sizeof p);
-}
-void bn254_g2_times(const uint8_t* xyzz, const uint8_t* k, int nbytes, uint8_t* out) {
-    PT p; memcpy(&p, xyzz, sizeof p);
-    PT r = PT::inf();
-    for (int i = nbytes * 8 - 1; i >= 0; i--) { r = PT::dbl(r); if ((k[i >> 3] >> (i & 7)) & 1) r.add(p); }
-    memcpy(out, &r, sizeof r);
-}
-int bn254_g2_gen_points(const uint8_t* gen_affine, uint64_t seed, uint64_t n, void* d_out, cudaStream_t stream) {
-    Affine<FT> g; memcpy(&g, gen_affine, sizeof g);
-    if (n) k_gen_points<FT><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g, seed, n, (Affine<FT>*)d_out);
-    return (int)cudaGetLastError();
-}
-int bn254_g2_precompute(const void* d_bases, uint64_t n, int c, int W, void* d_table, cudaStream_t stream) {
-    if (n) k_precompute<FT><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>((const Affine<FT>*)d_bases, n, c, W, (Affine<FT>*)d_table);
-    return (int)cudaGetLastError();
-}
-uint32_t bn254_g2_xyzz_bytes() { return (uint32_t)sizeof(PT); }
-}
+// MSM instantiation unit: bn254_g2 (coordinate field Fp2<BnFq>); the code is msm_group.inl
+#define SB_GROUP bn254_g2
+#define SB_FIELD Fp2<BnFq>
+#include "msm_group.inl"

@@ -23,7 +23,7 @@ struct MsmScratch; struct MsmLaunchStats; struct MsmSorted;
     void NAME##_from_affine(const uint8_t* aff, uint8_t* xyzz); \
     /* host: out = k * p, k plain little-endian scalar of nbytes */ \
     void NAME##_times(const uint8_t* xyzz, const uint8_t* k, int nbytes, uint8_t* out); \
-    /* async: n synthetic points k_i*G (k_i = SplitMix64(seed+i)|1) into d_out; gen = affine generator bytes (host) */ \
+    /* async: n synthetic points (k0(c) + j*kd)*G, see msm.cuh k_gen_points into d_out; gen = affine generator bytes (host) */ \
     int NAME##_gen_points(const uint8_t* gen_affine, uint64_t seed, uint64_t n, void* d_out, cudaStream_t stream); \
     /* async: table[w*n + i] = 2^(c*w) * bases[i], w < W (device pointers) */ \
     int NAME##_precompute(const void* d_bases, uint64_t n, int c, int W, void* d_table, cudaStream_t stream); \

@@ -59,8 +59,10 @@ template <class F> SB_HD F pl_pow(const PlonkPow<F>& t, uint64_t i) {
 // plain, so the Montgomery product is the plain value.  sig = (s1, s2) pairs, fac = (f1, f2) pairs, original order.
 template <class F> SB_HD void pl_addition(uint32_t i, const uint32_t* sig, const F* fac, F* w, uint32_t n_wit, uint32_t n_vars) {
     uint32_t s1 = sig[2 * i], s2 = sig[2 * i + 1];
-    F a = s1 < n_vars ? pl_ld(w + s1) : F::zero();               // getWitness :203-211
-    F b = s2 < n_vars ? pl_ld(w + s2) : F::zero();
+    // getWitness :203-211.  An addition that names itself or a later addition reads the reference's still-zero
+    // internalWitness slot (:178-180 allocate it zeroed); here that slot may be written concurrently, so it is forced to 0.
+    F a = (s1 < n_vars && (s1 < n_wit || s1 - n_wit < i)) ? pl_ld(w + s1) : F::zero();
+    F b = (s2 < n_vars && (s2 < n_wit || s2 - n_wit < i)) ? pl_ld(w + s2) : F::zero();
     pl_st(w + n_wit + i, F::add(F::mul(pl_ld(fac + 2 * i), a), F::mul(pl_ld(fac + 2 * i + 1), b)));
 }
 // computeWirePolynomials (:256-280): out[i] = toMontgomery(w[map[i]]) for i < n_cons, 0 up to n

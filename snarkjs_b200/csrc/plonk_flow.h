@@ -127,7 +127,8 @@ inline int plonk_parse_zkey(const uint8_t* d, uint64_t len, PlonkZkey& z, std::s
     z.X_2 = h + o;
     if (z.n < 8 || (z.n & (z.n - 1))) { err = "zkey: domain size is not a power of two"; return -1; }
     z.power = 0; while ((1u << z.power) < z.n) z.power++;
-    if (z.nAdditions > z.nVars || z.nConstraints > z.n || z.nPublic > z.nConstraints) { err = "zkey: inconsistent header"; return -1; }
+    if (z.nAdditions > z.nVars || z.nConstraints > z.n || z.nPublic > z.nConstraints ||
+        (uint64_t)z.nPublic + 1 > (uint64_t)z.nVars - z.nAdditions)   /* the public signals are witness[1..nPublic] */ { err = "zkey: inconsistent header"; return -1; }
     const uint64_t sd = (uint64_t)z.n * 32, npl = z.nPublic > 1 ? z.nPublic : 1;
     const uint64_t want[15] = {0, 0, 0, (uint64_t)z.nAdditions * 72, (uint64_t)z.nConstraints * 4, (uint64_t)z.nConstraints * 4, (uint64_t)z.nConstraints * 4,
                                5 * sd, 5 * sd, 5 * sd, 5 * sd, 5 * sd, 15 * sd, npl * 5 * sd, ((uint64_t)z.n + 6) * 2 * z.n8q};

@@ -1,6 +1,6 @@
 """Synthetic Groth16 workloads: the chain circuit x_{i+1} = x_i^2 + b with 2^L - 3 constraints
-(domain 2^L, nVars = 2^L, nPublic = 1) and a zkey whose base sets are random valid curve points generated on the
-GPU (sb_gen_points).  Such a key has no trusted-setup structure, so proofs do not verify, but CPU-vs-GPU parity and
+(domain 2^L, nVars = 2^L, nPublic = 1) and a zkey whose base sets are random valid curve points (generated on the
+GPU with sb_gen_points, or by any generator with the same definition).  Such a key has no trusted-setup structure, so proofs do not verify, but CPU-vs-GPU parity and
 throughput are well defined (every base is a full-size non-trivial point: the worst case for the MSMs)."""
 from __future__ import annotations
 
@@ -33,6 +33,18 @@ def chain_witness(r: int, L: int, x0: int = 3, b: int = 7) -> np.ndarray:
     return np.frombuffer(bytes(buf), np.uint8)
 
 
+def witness_like(witness: np.ndarray, seed: int = 7) -> np.ndarray:
+    """The scalar distribution of real circuits: 50 % zeros, 25 % ones, 25 % untouched; w[0] stays 1."""
+    wl = witness.reshape(-1, 32).copy()
+    kind = np.random.default_rng(seed).integers(0, 4, wl.shape[0])
+    wl[kind < 2] = 0
+    wl[kind == 2] = 0
+    wl[kind == 2, 0] = 1
+    wl[0] = 0
+    wl[0, 0] = 1
+    return wl.reshape(-1)
+
+
 def chain_coeffs(r: int, L: int) -> bytes:
     """zkey section 4 for the chain circuit: constraint i is x_i * x_i = x_{i+1} - b  (A and B rows: one entry each),
     plus the nPublic+1 public-input rows appended by setup (src/zkey_new.js:290-300).  Values are 1*R^2 mod r
@@ -58,21 +70,23 @@ def chain_coeffs(r: int, L: int) -> bytes:
     return struct.pack("<I", len(co)) + co.tobytes()
 
 
-def synth_groth16_zkey(curve: Curve, L: int, seed: int = 1) -> bytes:
-    """A Groth16 .zkey image (src/zkey_utils.js:20-45 layout) for the chain circuit with random valid bases."""
-    n8q, n8r = curve.n8q, 32
+def groth16_zkey_image(q: int, r: int, n8q: int, L: int, gen, seed: int = 1) -> bytes:
+    """A Groth16 .zkey image (src/zkey_utils.js:20-45 layout) for the chain circuit with random valid bases.
+    gen(group, seed, count) -> affine Montgomery bytes; bench.py passes the GPU generator (sb_gen_points) on the B200 arm
+    and the oracle's on the CPU reference arm — both produce the same points, hence byte-identical keys."""
+    n8r = 32
     n = 1 << L
     nVars, nPublic = n, 1
-    g1 = lambda s, k: gen_points(curve, 1, seed * 1000003 + s, k).tobytes()
-    g2 = lambda s, k: gen_points(curve, 2, seed * 1000003 + s, k).tobytes()
-    hdr = struct.pack("<I", n8q) + curve.q.to_bytes(n8q, "little") + struct.pack("<I", n8r) + curve.r.to_bytes(n8r, "little")
+    g1 = lambda s, k: bytes(gen(1, seed * 1000003 + s, k))
+    g2 = lambda s, k: bytes(gen(2, seed * 1000003 + s, k))
+    hdr = struct.pack("<I", n8q) + q.to_bytes(n8q, "little") + struct.pack("<I", n8r) + r.to_bytes(n8r, "little")
     hdr += struct.pack("<III", nVars, nPublic, n)
     hdr += g1(11, 1) + g1(12, 1) + g2(13, 1) + g2(14, 1) + g1(15, 1) + g2(16, 1)     # alpha1 beta1 beta2 gamma2 delta1 delta2
     secs = [
         (1, struct.pack("<I", 1)),
         (2, hdr),
         (3, g1(20, nPublic + 1)),
-        (4, chain_coeffs(curve.r, L)),
+        (4, chain_coeffs(r, L)),
         (5, g1(1 << 32, nVars)),
         (6, g1(2 << 32, nVars)),
         (7, g2(3 << 32, nVars)),
@@ -85,6 +99,11 @@ def synth_groth16_zkey(curve: Curve, L: int, seed: int = 1) -> bytes:
         out.append(struct.pack("<IQ", sid, len(payload)))
         out.append(payload)
     return b"".join(out)
+
+
+def synth_groth16_zkey(curve: Curve, L: int, seed: int = 1) -> bytes:
+    """groth16_zkey_image with the bases generated on the GPU."""
+    return groth16_zkey_image(curve.q, curve.r, curve.n8q, L, lambda grp, sd, k: gen_points(curve, grp, sd, k).tobytes(), seed)
 
 
 def wtns_container(r: int, witness: np.ndarray) -> bytes:

@@ -269,28 +269,107 @@ def test_groth16_errors(bn, golden):
 
 
 # ----------------------------------------------------------------------------------------------- synthetic workloads
-def _splitmix(x):
-    M = (1 << 64) - 1
-    x = (x + 0x9E3779B97F4A7C15) & M
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
-    return x ^ (x >> 31)
 
 
 @pytest.mark.parametrize("cname,cid", [("bn128", BN), ("bls12381", BLS)])
-def test_gen_points_are_k_times_generator(bn, bls, cname, cid):
+def test_gen_points_equal_the_oracle_generator(bn, bls, cname, cid):
+    """sb_gen_points and the oracle's incremental generator define the same points (bench.py builds the B200 arm's key
+    with the first and the CPU reference arm's key with the second): compared across a 4096-point chunk boundary, and
+    spot-checked as (k0 + j*kd)*G against the oracle's scalar multiplication."""
     from snarkjs_b200 import synth
     c = bn if cid == BN else bls
     ci = O.CURVES[cid]
-    for grp in (1, 2):
-        pts = synth.gen_points(c, grp, 42, 9).tobytes()
+    M = (1 << 64) - 1
+    for grp, n in ((1, 9000), (2, 4200)):
+        pts = synth.gen_points(c, grp, 42, n)
+        assert np.array_equal(pts, O.gen_points(cid, grp, 42, n)), (cname, grp)
         sz = ci.n8q * 2 * grp
         gen = ci.g1_affine_bytes(ci.g1) if grp == 1 else ci.g2_affine_bytes(ci.g2)
         gj = O.g_from_affine(cid, grp, gen)
-        for i in (0, 3, 8):
-            k = _splitmix(42 + i) | 1
-            want = O.g_to_affine(cid, grp, O.g_times(cid, grp, gj, k.to_bytes(8, "little")))
-            assert pts[i * sz:(i + 1) * sz] == want, (cname, grp, i)
+        kd = (42 * 2654435761 + 12345) & M
+        for i in (0, 3, 4095, 4096, 4199):
+            ch, j = divmod(i, 4096)
+            k = (((42 ^ 0x9E3779B97F4A7C15) + ch * 0xD1B54A32D192ED03) & M) + j * kd
+            want = O.g_to_affine(cid, grp, O.g_times(cid, grp, gj, k.to_bytes(16, "little")))
+            assert pts.tobytes()[i * sz:(i + 1) * sz] == want, (cname, grp, i)
+
+
+@pytest.mark.parametrize("L", [12, 16, 18])
+def test_bench_key_proof_hash_matches_committed_oracle_hash(bn, L):
+    """The key bench.py proves (synth seed 1, r = 5, s = 7): the GPU proof object hashes to the CPU oracle's committed
+    hash (tests/golden/bench_proof_hashes.json, written by make_bench_hashes.py without a GPU).  bench.py asserts the
+    2^20 / 2^22 entries of the same table on every run."""
+    import json, os, hashlib
+    from snarkjs_b200 import groth16, synth
+    tab = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench_proof_hashes.json")))["groth16_bn128_chain_r5_s7"]
+    zkey = synth.synth_groth16_zkey(bn, L, seed=1)
+    ci = O.CURVES[BN]
+    pk = groth16.ProvingKey(zkey, curve=bn)
+    aff = pk.prove_raw(synth.chain_witness(bn.r, L), ci.fr_to_mont(5), ci.fr_to_mont(7))
+    obj = groth16.proof_to_object(bn, aff)
+    pk.release()
+    assert hashlib.sha256(json.dumps(obj, sort_keys=True, separators=(",", ":")).encode()).hexdigest() == tab[str(L)]
+
+
+def test_overlapping_calls_on_one_context_are_serialised(bn):
+    """The reference awaits several bulk calls at once (build/snarkjs.js:14653, 14929-14932) and an N-API shim runs them
+    on libuv threads: four threads hammer ONE context with NTTs, MSMs and joinABC calls that share its staging and io
+    buffers; every result must equal the single-threaded one."""
+    import threading
+    x = [rand_fr(900 + i, 1 << 14) for i in range(4)]
+    bases = O.gen_points(BN, 1, 77, 1 << 12)
+    want_ntt = [bn.Fr.fft(v).copy() for v in x]
+    want_msm = [bn.G1.toAffine(bn.G1.multiExpAffine(bases, v[:32 << 12])).tobytes() for v in x]
+    from snarkjs_b200.curve import _ptr
+
+    def join():
+        out = np.empty_like(x[0])
+        bn.check(bn.lib.sb_qap_join_abc(bn.handle, _ptr(x[0]), _ptr(x[1]), _ptr(x[2]), x[0].size // 32, _ptr(out)))
+        return out
+    want_join = join()
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(6):
+                assert np.array_equal(bn.Fr.fft(x[i]), want_ntt[i])
+                assert bn.G1.toAffine(bn.G1.multiExpAffine(bases, x[i][:32 << 12])).tobytes() == want_msm[i]
+                assert np.array_equal(join(), want_join)
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+
+def test_prove_resident_needs_a_witness_and_truncated_containers_fail(bn, golden):
+    import ctypes, struct
+    from snarkjs_b200 import groth16, SbError
+    from snarkjs_b200.curve import _ptr
+    g = golden("groth16_case.npz")
+    zkey = g["zkey"].tobytes()
+    pk = groth16.ProvingKey(zkey, curve=bn)
+    out = np.empty(256, np.uint8)
+    ci = O.CURVES[BN]
+    rc = bn.lib.sb_groth16_prove_resident(bn.handle, pk.handle, ci.fr_to_mont(1), ci.fr_to_mont(2), _ptr(out))
+    assert rc != 0 and b"no witness resident" in bn.lib.sb_last_error(bn.handle)
+    pk.release()
+    # a section length near 2^64 must not wrap the bounds check (ADVICE r1): zkey and wtns containers
+    sid, ln = struct.unpack_from("<IQ", zkey, 12)
+    bad = bytearray(zkey)
+    struct.pack_into("<Q", bad, 16, (1 << 64) - 12 - 12)
+    h = ctypes.c_uint64()
+    buf = np.frombuffer(bytes(bad), np.uint8)
+    assert bn.lib.sb_groth16_load(bn.handle, _ptr(buf), buf.size, ctypes.byref(h)) != 0
+    assert b"Invalid file size" in bn.lib.sb_last_error(bn.handle)
+    w = bytearray(g["wtns"].tobytes())
+    struct.pack_into("<Q", w, 16, (1 << 64) - 24)
+    pk = groth16.ProvingKey(zkey, curve=bn)
+    wb = np.frombuffer(bytes(w), np.uint8)
+    assert bn.lib.sb_groth16_prove_wtns(bn.handle, pk.handle, _ptr(wb), wb.size, ci.fr_to_mont(1), ci.fr_to_mont(2), _ptr(out)) != 0
+    pk.release()
 
 
 def test_groth16_synthetic_2_16_matches_oracle(bn):

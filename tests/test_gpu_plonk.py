@@ -62,7 +62,6 @@ def test_plonk_synthetic(env, n_gates, structured):
         pk.release()
 
 
-@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
 @pytest.mark.parametrize("n_gates,n_pub,with_additions", [(29, 3, True), (60, 5, False)])
 def test_plonk_shapes(env, n_gates, n_pub, with_additions):
     """Several public inputs (PI(X) sums several Lagrange polynomials) and a key without additions."""
@@ -79,7 +78,6 @@ def test_plonk_shapes(env, n_gates, n_pub, with_additions):
         pk.release()
 
 
-@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
 def test_plonk_reference_circuit2(env, golden, reference_plonk_key):
     """The reference's larger PLONK key (test/circuit2: domain 2048, 1001 additions, 4 public signals; rebuilt byte for byte
     from its r1cs) with the reference's own witness."""
@@ -93,7 +91,6 @@ def test_plonk_reference_circuit2(env, golden, reference_plonk_key):
         pk.release()
 
 
-@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
 def test_plonk_deep_addition_chain(env):
     """Every addition depends on the previous one: one k_pl_additions launch per addition (dependency levels)."""
     op = env["op"]
@@ -126,7 +123,6 @@ def test_plonk_bls12381(env):
         curve.terminate()
 
 
-@pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")
 def test_plonk_key_from_file(env, golden, tmp_path):
     """sb_plonk_load_file: the key mapped from disk gives the same proof as the key loaded from bytes."""
     g = golden("plonk_case.npz")

@@ -5,11 +5,8 @@ import json
 
 import pytest
 
-# This file sorts after the other GPU suites on purpose.  First hardware run (profiles/fflonk_first_gpu_run_r1.log, the
-# round's last 81 s of GPU budget): the reference fixture and the first three synthetic keys passed before the time limit
-# cut the run; the cases that had not finished are non-strict xfail until they have a recorded green run.
+# All cases have a recorded green hardware run (GPUTEST_r01.json, driver run at the end of round 1).
 pytestmark = pytest.mark.gpu
-NOT_YET_RUN = pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (round-1 GPU budget exhausted)")
 
 BLINDERS = [0x6000 + 32452843 * i for i in range(9)]
 
@@ -44,7 +41,7 @@ def test_fflonk_reference_fixture(env, golden):
 
 
 @pytest.mark.parametrize("n_gates,n_pub,with_additions", [(13, 1, True), (120, 3, True), (500, 1, False),
-                                                          pytest.param(2000, 1, True, marks=NOT_YET_RUN)])
+                                                          (2000, 1, True)])
 def test_fflonk_synthetic(env, n_gates, n_pub, with_additions):
     """2000 gates -> domain 2048, 18450 PTau points: the MSMs run in table mode."""
     op, off = env["op"], env["off"]
@@ -63,7 +60,6 @@ def test_fflonk_synthetic(env, n_gates, n_pub, with_additions):
         pk.release()
 
 
-@NOT_YET_RUN
 def test_fflonk_key_from_file(env, golden, tmp_path):
     g = golden("fflonk_case.npz")
     zkey, wtns = bytes(g["zkey"]), bytes(g["wtns"])
@@ -76,7 +72,6 @@ def test_fflonk_key_from_file(env, golden, tmp_path):
         pk.release()
 
 
-@NOT_YET_RUN
 def test_fflonk_errors(env, golden):
     sb, op, off, orc = env["sb"], env["op"], env["off"], env["orc"]
     g = golden("fflonk_case.npz")

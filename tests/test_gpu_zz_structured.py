@@ -1,10 +1,9 @@
 """GPU: Groth16 proofs from sb_groth16_prove on structured synthetic keys (oracle/synth_setup.py) equal the oracle's and
-VERIFY under the pairing check — on BN254 and on BLS12-381, where the reference ships no fixtures.  Added after the
-round-1 GPU budget was spent: non-strict xfail until a hardware run is recorded (profiles/README.md); sorts last."""
+VERIFY under the pairing check — on BN254 and on BLS12-381, where the reference ships no fixtures (green on the B200 since
+the round-1 driver run, GPUTEST_r01.json)."""
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="no recorded hardware run yet (added after the round-1 GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["bn128", "bls12381"])
