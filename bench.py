@@ -210,9 +210,14 @@ def run_b200(args):
     s = (7 * (1 << 256) % curve.r).to_bytes(32, "little")
     proof = np.empty(8 * curve.n8q, np.uint8)
     lib, h = curve.lib, curve.handle
-    pbytes = lib.sb_groth16_partials_bytes(h)
-    partial = np.empty(pbytes, np.uint8)
-    gather = [torch.empty(pbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if world > 1 else None
+    if world > 1:
+        # the library's own communicator (NCCL inside libsnarkb200.so): torch.distributed only carries the 128-byte id
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(curve.comm_unique_id()), dtype=torch.uint8).clone()
+        idt = idt.cuda()
+        dist.broadcast(idt, 0)
+        curve.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
 
     def step(resident: bool):
         if world == 1:
@@ -220,13 +225,8 @@ def run_b200(args):
                 curve.check(lib.sb_groth16_prove_resident(h, pk.handle, r, s, _ptr(proof)))
             else:
                 curve.check(lib.sb_groth16_prove(h, pk.handle, wptr, nwit, r, s, _ptr(proof)))
-        else:
-            curve.check(lib.sb_groth16_prove_shard(h, pk.handle, None if resident else wptr, nwit, rank, world, _ptr(partial)))
-            mine = torch.from_numpy(partial).cuda()
-            dist.all_gather(gather, mine)                        # the path's one exchange step (NCCL, KB-scale)
-            if rank == 0:
-                allp = torch.cat(gather).cpu().numpy()
-                curve.check(lib.sb_groth16_finish(h, pk.handle, _ptr(allp), world, r, s, _ptr(proof)))
+        else:   # one collective call: witness slices + all-gather, chain exchange, partial all-gather all inside the library
+            curve.check(lib.sb_groth16_prove_dist(h, pk.handle, None if resident else wptr, nwit, r, s, _ptr(proof) if rank == 0 else None))
 
     def sync():
         torch.cuda.synchronize()
@@ -258,6 +258,29 @@ def run_b200(args):
         brk = {"h2d_witness": curve.last_ms(1), "device_total": curve.last_ms(0)}
         dt_res = timed(lambda: step(True), args.steps)
     clocks = cs.summary()
+    replicas = None
+    if world > 1:
+        # N independent provers (SURVEY §8e "8 independent provers"): every rank proves its own copy of the workload with
+        # a full key; no exchange at all.  Reported beside the sharded single-proof rate.
+        pk_full = groth16.ProvingKey(zkey, curve=curve)
+        rproof = np.empty(8 * curve.n8q, np.uint8)
+
+        def rstep(resident):
+            if resident:
+                curve.check(lib.sb_groth16_prove_resident(h, pk_full.handle, r, s, _ptr(rproof)))
+            else:
+                curve.check(lib.sb_groth16_prove(h, pk_full.handle, wptr, nwit, r, s, _ptr(rproof)))
+        for _ in range(3):
+            rstep(False)
+        dt_r_e2e = timed(lambda: rstep(False), args.steps)
+        dt_r_res = timed(lambda: rstep(True), args.steps)
+        same = torch.tensor([1 if (rank != 0 or np.array_equal(rproof, proof_e2e)) else 0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        replicas = {"value": world * args.steps / dt_r_res, "unit": "proofs/s", "e2e": world * args.steps / dt_r_e2e,
+                    "ms_per_proof_per_gpu": dt_r_res / args.steps * 1e3, "scaling": "weak",
+                    "same_proof_as_sharded": bool(same.item()),
+                    "note": f"{world} independent provers, one full key per GPU, each proving its own copy of the workload"}
+        pk_full.release()
     # kernel-level numbers for the rooflines: one extra proof with every stream serialised (in the overlapped schedule
     # kernels share the SMs, so their event-bracketed durations are not per-kernel costs)
     lib.sb_set_tuning(2, 1)
@@ -316,10 +339,10 @@ def run_b200(args):
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "u32x8 (256-bit modular integers, 32-bit limbs)", "data": "synthetic",
         "config": {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{L} (nVars 2^{L}, {2 * ((1 << L) - 3) + 2} QAP coefficients); 4 G1 MSM + 1 G2 MSM of 2^{L} points, 6 NTT of 2^{L}",
-                   "curve": "bn128", "witness": "witness-like (50% zeros, 25% ones)" if args.witness_like else "uniform field elements (chain circuit)", "parallelism": f"msm point-range shards x{world}" if world > 1 else "single GPU",
+                   "curve": "bn128", "witness": "witness-like (50% zeros, 25% ones)" if args.witness_like else "uniform field elements (chain circuit)", "parallelism": f"one proof over {world} GPUs: MSM point-range shards, A/B/C transform chains on ranks 0..2, NCCL exchange inside the library" if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (384 MiB of bases + 32 MiB witness per proof vs 126 MB L2)"},
         "e2e": {"value": args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": int(nwit * 32), "d2h_bytes_per_step": int(proof.size),
-                "ms_per_step": dt_e2e / args.steps * 1e3, "api": "sb_groth16_prove (pinned host witness -> affine proof bytes on host)"},
+                "ms_per_step": dt_e2e / args.steps * 1e3, "api": ("sb_groth16_prove_dist (pinned host witness on every rank, 1/N uploaded per rank -> affine proof bytes on rank 0's host)" if world > 1 else "sb_groth16_prove (pinned host witness -> affine proof bytes on host)")},
         "gpu_launches": int(l1 - l0),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": name, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak if hbm_peak else None,
@@ -330,13 +353,17 @@ def run_b200(args):
                          "peak_source": "sb_calibrate(1): four independent per-thread BN254 Fq Montgomery-multiply chains (IMAD.WIDE.U32.X issue-bound), measured on this GPU in this run",
                          "imad_wide_per_s": peak_imad, "imad_wide_per_clk_per_sm": (peak_imad / 148.0 / (clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
                          "all_accumulate_kernels_frac": (all_mod / (all_ms * 1e-3)) / peak_modmul if (all_ms > 0 and peak_modmul > 0) else None},
-        "breakdown_ms": brk, "accumulate": acc, "setup_s": t_setup,
+        "breakdown_ms": brk, "accumulate": acc, "setup_s": t_setup, "replicas": replicas,
         "proof_sha256": ph,                      # same inputs => same bytes at every N
         "oracle_match": (ph == gold) if gold else None,
         "oracle_match_source": "tests/golden/bench_proof_hashes.json (CPU oracle proof of this key, made by tests/golden/make_bench_hashes.py)" if gold else "no committed oracle hash for this size",
     }
     if gold and ph != gold:
         line["oracle_mismatch"] = {"got": ph, "want": gold}
+    if args.mode == "replicas" and replicas:      # report the independent-prover rate as `value`, the sharded one beside it
+        line["sharded"] = {"value": line["value"], "e2e": line["e2e"]["value"], "ms_per_step": line["ms_per_step"], "scaling": "strong"}
+        line["value"], line["ms_per_step"], line["scaling"] = replicas["value"], 1e3 / replicas["value"], "weak"
+        line["e2e"]["value"] = replicas["e2e"]
     if not args.no_cpu_baseline and world == 1:
         try:   # the CPU oracle proves the SAME key and witness (full size unless --cpu-log-n): baseline + live parity check
             Ls = args.cpu_log_n or L

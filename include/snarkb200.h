@@ -141,6 +141,30 @@ uint32_t sb_groth16_partials_bytes(sb_ctx* ctx);
 int sb_groth16_finish(sb_ctx* ctx, uint64_t handle, const uint8_t* partials_all_ranks, int n_shards,
                       const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
 
+/* ---- multi-GPU inside the library (SURVEY §8b "NCCL comm built here", §8e) -------------------------------------------
+ * One context per GPU, one NCCL rank per context.  libnccl.so.2 is dlopen'ed on first use (a copy already loaded in the
+ * process, e.g. torch's, is reused), so single-GPU hosts need no NCCL.
+ *   multi-process (one process per GPU, torchrun / a Node cluster): rank 0 calls sb_comm_unique_id and hands the 128 bytes
+ *     to the other processes over any channel; every rank calls sb_comm_init_rank, loads its key shard with
+ *     sb_groth16_load_sharded(rank, world) and then sb_groth16_prove_dist per proof (a collective call).
+ *   single process: sb_create_multi / sb_groth16_load_multi / sb_groth16_prove_multi do the same with one host thread per
+ *     device — the _multiExp chunk fan-out (14636-14658) and the worker pool (14064-14232) replaced by GPUs.
+ * What a distributed proof exchanges: each rank uploads 1/world of the witness and an all-gather over NVLink completes it;
+ * the iNTT -> coset-NTT chains of A, B, C run on ranks sb_dist_chain_owner(0..2) and their evaluations are sent to the rank
+ * that owns each H range; every rank multiplies its point range of the five base sets; one all-gather of the (A, C', B2)
+ * partials (a few hundred bytes) ends the proof.  Proof bytes equal the single-GPU ones. */
+int sb_comm_unique_id(uint8_t out[128]);
+int sb_comm_init_rank(sb_ctx* ctx, int world, int rank, const uint8_t id[128]);
+int sb_comm_info(sb_ctx* ctx, int* rank, int* world);      /* world = 0 when the context has no communicator */
+int sb_comm_destroy(sb_ctx* ctx);
+int sb_dist_chain_owner(int chain, int world);
+int sb_groth16_prove_dist(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness,
+                          const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out_or_null);
+int sb_create_multi(int curve, const int* device_ids, int n_devices, sb_ctx** out_contexts);
+int sb_groth16_load_multi(sb_ctx* const* ctxs, int n, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handles_out);
+int sb_groth16_prove_multi(sb_ctx* const* ctxs, const uint64_t* handles, int n, const uint8_t* witness, uint64_t n_witness,
+                           const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out);
+
 /* Host-only halves of the multi-GPU path (no context, no device needed): combine partials gathered from the ranks and
  * assemble the proof (src/groth16_prove.js:103-132).  partial = extended-Jacobian X,Y,ZZ,ZZZ Montgomery bytes;
  * Groth16 partial block = A | B1 | C | H (G1) | B2 (G2). */
@@ -165,7 +189,9 @@ int sb_dev_download(sb_ctx* ctx, uint8_t* dst, const void* src_dev, uint64_t byt
  * sb_plonk_prove / sb_fflonk_prove: 1..5 = host wall clock of rounds 1..5 (each round ends on a synchronising commit). */
 float sb_last_ms(sb_ctx* ctx, int which);
 /* counters of the last MSM / prove call: 0/1 = summed device time (ms) of the G1 / G2 bucket-accumulation kernel
- * launches, 2/3 = number of those launches, 4/5 = (scalar digit, point) entries they consumed. */
+ * launches, 2/3 = number of those launches, 4/5 = (scalar digit, point) entries they consumed; 8..15 = device time (ms) per
+ * kernel class: digits + radix sort, G1 accumulation, G2 accumulation, head folding, bucket reduction + window sums,
+ * QAP rows, NTT passes, joinABC (meaningful per class when the call ran serialised, sb_set_tuning(2, 1)). */
 double sb_last_stat(sb_ctx* ctx, int which);
 /* integer-pipe calibration on this device: what = 0 -> IMAD.WIDE.U32 per second, 1 -> register-resident BN254 Fq
  * Montgomery multiplies per second (the modmul-bound roofline denominators). */

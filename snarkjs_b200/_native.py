@@ -67,6 +67,15 @@ _SIGNATURES = {
     "sb_groth16_prove_shard": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_int, ctypes.c_int, vp]),
     "sb_groth16_partials_bytes": (u32, [vp]),
     "sb_groth16_finish": (ctypes.c_int, [vp, u64, vp, ctypes.c_int, vp, vp, vp]),
+    "sb_comm_unique_id": (ctypes.c_int, [vp]),
+    "sb_comm_init_rank": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
+    "sb_comm_info": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "sb_comm_destroy": (ctypes.c_int, [vp]),
+    "sb_dist_chain_owner": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "sb_groth16_prove_dist": (ctypes.c_int, [vp, u64, vp, u64, vp, vp, vp]),
+    "sb_create_multi": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(vp)]),
+    "sb_groth16_load_multi": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, vp, u64, ctypes.POINTER(u64)]),
+    "sb_groth16_prove_multi": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.POINTER(u64), ctypes.c_int, vp, u64, vp, vp, vp]),
     "sb_host_sum_partials": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp]),
     "sb_host_partial_from_affine": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp]),
     "sb_host_partial_bytes": (u32, [ctypes.c_int, ctypes.c_int]),

@@ -9,6 +9,10 @@
 #include <map>
 #include <algorithm>
 #include <mutex>
+#include <future>
+#include <thread>
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: the library is dlopen'ed on first use (no link-time dependency)
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/mman.h>
@@ -111,7 +115,10 @@ struct sb_ctx {
     std::vector<uint8_t> nqr, shift;
     std::vector<uint8_t> gen1, gen2;            // affine generators, Montgomery
     cudaEvent_t prof_ev[64];
-    double stat[8] = {0};                        // see sb_last_stat
+    double stat[16] = {0};                       // see sb_last_stat
+    // multi-GPU (sb_comm_init_rank): one NCCL rank per context
+    ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    void* d_xchg = nullptr; uint8_t* h_xchg = nullptr;   // partial exchange: world x partial bytes (device / pinned)
 };
 
 namespace {
@@ -334,9 +341,12 @@ void init_generators(sb_ctx* c) {
 void prof_begin(sb_ctx* c) { c->stats.ev = c->prof_ev; c->stats.nev = 64; c->stats.used = 0; for (double& d : c->stat) d = 0; }
 void prof_end(sb_ctx* c) {
     for (int i = 0; i + 1 < c->stats.used; i += 2) {
-        float ms = 0; cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]);
-        int g = c->stats.tag[i / 2];
-        if (g == SB_G1) { c->stat[0] += ms; c->stat[2] += 1; } else { c->stat[1] += ms; c->stat[3] += 1; }
+        float ms = 0; if (cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        const int g = c->stats.tag[i / 2];
+        if (g == PROF_ACC_G1) { c->stat[0] += ms; c->stat[2] += 1; c->stat[9] += ms; }
+        else if (g == PROF_ACC_G2) { c->stat[1] += ms; c->stat[3] += 1; c->stat[10] += ms; }
+        else if (g == PROF_SORT) c->stat[8] += ms;
+        else if (g >= PROF_FOLD && g <= PROF_JOIN) c->stat[11 + (g - PROF_FOLD)] += ms;
     }
     c->stats.ev = nullptr; c->stats.used = 0;
 }
@@ -471,7 +481,8 @@ template <class PR> static void fr_neg_mul_bytes(const uint8_t* r, const uint8_t
 // ================================================================================================================
 extern "C" {
 
-const char* sb_version(void) { return "snarkb200 0.1 (sm_100a)"; }
+const char* sb_version(void) { return "snarkb200 0.2 (sm_100a)"; }
+int sb_comm_destroy(sb_ctx* c);
 
 int sb_create(int curve, int device_id, sb_ctx** out) {
     if (!out || (curve != SB_BN254 && curve != SB_BLS12_381)) return SB_ERR_ARG;
@@ -503,6 +514,7 @@ int sb_create(int curve, int device_id, sb_ctx** out) {
 
 void sb_destroy(sb_ctx* c) {
     if (!c) return;
+    sb_comm_destroy(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto* k : c->keys) if (k) free_key(k);
@@ -704,7 +716,7 @@ int sb_set_tuning(int key, int value) {
     if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
     if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
 }
-double sb_last_stat(sb_ctx* c, int which) { SB_LOCK(c); return (c && which >= 0 && which < 8) ? c->stat[which] : 0.0; }
+double sb_last_stat(sb_ctx* c, int which) { SB_LOCK(c); return (c && which >= 0 && which < 16) ? c->stat[which] : 0.0; }
 double sb_calibrate(sb_ctx* c, int what) { SB_LOCK(c); if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
 int sb_gen_points(sb_ctx* c, int group, uint64_t seed, uint64_t n, uint8_t* out) { SB_LOCK(c);
     if (!c || (group != SB_G1 && group != SB_G2)) return SB_ERR_ARG;
@@ -874,7 +886,7 @@ static int groth16_load_impl(sb_ctx* c, ZkeySource& src, int shard, int n_shards
     up((void**)&k->d_rowptr, rowptr.data(), rowptr.size() * 8, rowptr.size() * 8);
     up((void**)&k->d_sig, sig.data(), (size_t)ncoef * 4, (size_t)ncoef * 4);
     up(&k->d_coef, coef.data(), (size_t)ncoef * 32, (size_t)ncoef * 32);
-    up(&k->dW, nullptr, 0, nv * 32);
+    up(&k->dW, nullptr, 0, (nv + 64) * 32);   // + room for the padded slices of the distributed witness all-gather
     up(&k->dA_T, nullptr, 0, n * 32); up(&k->dB_T, nullptr, 0, n * 32); up(&k->dC_T, nullptr, 0, n * 32); up(&k->dTmp, nullptr, 0, n * 32);
     up(&k->dTmp2, nullptr, 0, n * 32); up(&k->dTmp3, nullptr, 0, n * 32);
     up(&k->dWsum, nullptr, 0, 8 * 80 * 4 * 96);
@@ -925,64 +937,208 @@ int sb_groth16_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
 }
 uint32_t sb_groth16_partials_bytes(sb_ctx* c) { return c ? 4 * c->g1.xyzz_bytes + c->g2.xyzz_bytes : 0; }
 
+// ---------------------------------------------------------------------------------------------------- NCCL
+// libnccl is opened on first use, so libsnarkb200.so loads (and every single-GPU entry works) on hosts without NCCL.
+// If the process already has a libnccl.so.2 (torch bundles one) that copy is reused.
+struct NcclApi {
+    void* so = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api(std::string* why) {
+    static std::mutex mu; static NcclApi api; static bool tried = false; static std::string err;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tried) {
+        tried = true;
+        const char* env = getenv("SB_NCCL_LIB");
+        void* so = env ? dlopen(env, RTLD_NOW | RTLD_LOCAL) : nullptr;
+        if (!so) so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!so) so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!so) err = std::string("cannot load libnccl.so.2: ") + dlerror();
+        else {
+            api.so = so;
+            bool ok = true;
+            auto sym = [&](const char* n) { void* p = dlsym(so, n); if (!p) { ok = false; err = std::string("libnccl: missing symbol ") + n; } return p; };
+            api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+            api.Send = (decltype(api.Send))sym("ncclSend");
+            api.Recv = (decltype(api.Recv))sym("ncclRecv");
+            api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+            if (!ok) api.so = nullptr;
+        }
+    }
+    if (!api.so) { if (why) *why = err; return nullptr; }
+    return &api;
+}
+#define NC(c, api, call) do { ncclResult_t _r = (call); if (_r != ncclSuccess) return fail(c, SB_ERR_CUDA, std::string(#call) + ": " + (api)->GetErrorString(_r)); } while (0)
+
+int sb_comm_unique_id(uint8_t out[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!out) return SB_ERR_ARG;
+    NcclApi* nc = nccl_api(nullptr); if (!nc) return SB_ERR_CUDA;
+    ncclUniqueId id; if (nc->GetUniqueId(&id) != ncclSuccess) return SB_ERR_CUDA;
+    memcpy(out, &id, 128); return 0;
+}
+int sb_comm_init_rank(sb_ctx* c, int world, int rank, const uint8_t id_bytes[128]) { SB_LOCK(c);
+    if (!c || !id_bytes || world < 1 || world > 64 || rank < 0 || rank >= world) return fail(c, SB_ERR_ARG, "invalid communicator arguments");
+    if (c->comm) return fail(c, SB_ERR_ARG, "context already belongs to a communicator");
+    std::string why; NcclApi* nc = nccl_api(&why); if (!nc) return fail(c, SB_ERR_CUDA, why);
+    cudaSetDevice(c->device);
+    ncclUniqueId id; memcpy(&id, id_bytes, 128);
+    NC(c, nc, nc->CommInitRank(&c->comm, world, id, rank));
+    c->rank = rank; c->world = world;
+    const size_t pb = (size_t)sb_groth16_partials_bytes(c);
+    CU(c, cudaMalloc(&c->d_xchg, pb * world));
+    CU(c, cudaHostAlloc((void**)&c->h_xchg, pb * (world + 1), cudaHostAllocDefault));
+    return 0;
+}
+int sb_comm_info(sb_ctx* c, int* rank, int* world) { SB_LOCK(c);
+    if (!c) return SB_ERR_ARG;
+    if (rank) *rank = c->rank; if (world) *world = c->comm ? c->world : 0;
+    return 0;
+}
+int sb_comm_destroy(sb_ctx* c) { SB_LOCK(c);
+    if (!c) return SB_ERR_ARG;
+    if (c->comm) {
+        cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
+        if (NcclApi* nc = nccl_api(nullptr)) nc->CommDestroy(c->comm);
+        c->comm = nullptr; c->rank = 0; c->world = 1;
+        if (c->d_xchg) cudaFree(c->d_xchg); if (c->h_xchg) cudaFreeHost(c->h_xchg);
+        c->d_xchg = nullptr; c->h_xchg = nullptr;
+    }
+    return 0;
+}
+// which rank runs the iNTT -> coset NTT chain of polynomial j (0 = A, 1 = B, 2 = C) when a proof is distributed
+int sb_dist_chain_owner(int chain, int world) { return world > 0 ? chain % world : 0; }
+
+// plain (non-Montgomery) r and s: when given, the prover folds s*A + r*B1 + H into the C partial as soon as A and B1 land
+// (hidden behind the C and H MSMs), so that the proof assembly after the last MSM is three additions
+struct ProofScalars { uint8_t rp[32], sp[32]; };
+
 // device part of the prover: returns the five MSM partials (A, B1, C, H | B2) as host XYZZ bytes.
-static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials) {
+// dist: this context is rank c->rank of c->world (sb_comm_init_rank); the witness is uploaded in slices and all-gathered,
+// the three transform chains run on different ranks and exchange their coset evaluations (NCCL send/recv), every rank
+// then joins and multiplies its own H range.
+static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials,
+                          const ProofScalars* ps = nullptr, bool dist = false) {
     if (witness && n_witness != k->nVars) return fail(c, SB_ERR_ARG, "Invalid witness length. Circuit: " + std::to_string(k->nVars) + ", witness: " + std::to_string(n_witness));
     cudaSetDevice(c->device);
     const uint64_t n = k->domainSize, nv = k->nVars;
     const int cv = c->curve;
+    NcclApi* nc = nullptr;
+    if (dist) {
+        if (!c->comm) return fail(c, SB_ERR_ARG, "context has no communicator: call sb_comm_init_rank first");
+        nc = nccl_api(nullptr);
+        shard = c->rank; n_shards = c->world;
+    }
+    const int world = n_shards, rank = shard;
     int rc;
     tick(c, 0);
-    if (witness) { k->witness_resident = false; CU(c, h2d(c, k->dW, witness, nv * 32)); k->witness_resident = true; }
-    else if (!k->witness_resident) return fail(c, SB_ERR_ARG, "no witness resident for this proving key: call sb_groth16_prove first");
+    if (witness) {
+        k->witness_resident = false;
+        if (dist && world > 1) {   // every rank uploads 1/world of the witness; NVLink all-gather completes it
+            const uint64_t per = (nv + world - 1) / world, lo = std::min(nv, per * (uint64_t)rank), cnt = std::min(nv - lo, per);
+            CU(c, h2d(c, (uint8_t*)k->dW + lo * 32, witness + lo * 32, cnt * 32));
+            NC(c, nc, nc->AllGather((const uint8_t*)k->dW + per * rank * 32, k->dW, per * 32, ncclUint8, c->comm, c->stream));
+        } else CU(c, h2d(c, k->dW, witness, nv * 32));
+        k->witness_resident = true;
+    } else if (!k->witness_resident) return fail(c, SB_ERR_ARG, "no witness resident for this proving key: call sb_groth16_prove first");
     tick(c, 1);
     prof_begin(c);
-    void* tmp = k->dTmp;
-    auto run_qap_ntt = [&]() -> int {
-    // buildABC1 (:147-187)
-    rc = fr_qap_rows(cv, k->d_rowptr, k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, n, c->stream); c->launches++;
-    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_qap_rows");
-    // :64-76  ifft -> batchApplyKey(1, inc) -> fft, with 1/n of the inverse folded into the coset table
-    const uint8_t* inc = (k->power == c->fr_s) ? c->shift.data() : c->roots[k->power + 1].data();
-    uint8_t ninv[32];
-    if (cv == SB_BN254) ninv_bytes<BnFr>(k->power, ninv); else ninv_bytes<BlsFr>(k->power, ninv);
-    FrPre pre; rc = get_pre(c, n, ninv, inc, &pre); if (rc) return rc;
-    // the three transforms run as one batch per pass (A, B, C together: grids fill whole waves)
-    void* odd[3]; void* bufs[3] = {k->dA_T, k->dB_T, k->dC_T}; void* scr[3] = {k->dTmp, k->dTmp2, k->dTmp3};
-    {
-        FrNttTables tbi, tbf;
-        rc = get_ntt_tab(c, k->power, true, &tbi); if (rc) return rc;
-        rc = get_ntt_tab(c, k->power, false, &tbf); if (rc) return rc;
-        int side = 0, launches = 0;
-        rc = fr_ntt_batch(cv, bufs, scr, 3, k->power, &tbi, nullptr, nullptr, c->stream, &side, &launches);      // unscaled inverse
-        if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt_batch");
-        void** src = side ? scr : bufs; void** dst = side ? bufs : scr;
-        int side2 = 0;
-        rc = fr_ntt_batch(cv, src, dst, 3, k->power, &tbf, &pre, nullptr, c->stream, &side2, &launches);         // coset NTT, 1/n folded in
-        if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt_batch");
-        c->launches += launches;
-        void** res = side2 ? dst : src; void** fre = side2 ? src : dst;
-        for (int i = 0; i < 3; i++) odd[i] = res[i];
-        tmp = fre[0];                                     // a buffer that holds no result: output of joinABC
-    }
-    // joinABC (:320-374) -> plain scalars for the H MSM, written over the remaining scratch buffer
-    rc = fr_join_abc(cv, odd[0], odd[1], odd[2], tmp, n, c->stream); c->launches++;
-    if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_join_abc");
-    return 0;
-    };
     // MSMs (:84-101).  Shard = contiguous point range; shard 0 of 1 = everything.
-    auto range = [&](uint64_t total, uint64_t& lo, uint64_t& cnt) { sb_shard_range(total, shard, n_shards, &lo, &cnt); };
+    auto range_of = [&](uint64_t total, int sh, uint64_t& lo, uint64_t& cnt) { sb_shard_range(total, sh, n_shards, &lo, &cnt); };
+    uint64_t wlo, wcnt; range_of(nv, rank, wlo, wcnt);
+    uint64_t hlo, hcnt; range_of(n, rank, hlo, hcnt);
+    // chain j (0 = A, 1 = B, 2 = C) runs on rank owner(j); without a communicator every chain runs here
+    auto owner = [&](int j) { return (dist && world > 1) ? sb_dist_chain_owner(j, world) : rank; };
+    void* bufs[3] = {k->dA_T, k->dB_T, k->dC_T}; void* scr[3] = {k->dTmp, k->dTmp2, k->dTmp3};
+    // where the chain results end up depends only on the pass count: known on ranks that run no chain too
+    const int np = fr_ntt_passes(k->power);
+    void* odd[3]; void* tmp;
+    { const bool x_scr = (np & 1) != 0;                          // after the inverse transform the data sits in scr iff np is odd
+      for (int j = 0; j < 3; j++) { void* X = x_scr ? scr[j] : bufs[j]; void* Y = x_scr ? bufs[j] : scr[j]; odd[j] = (np & 1) ? Y : X; }
+      tmp = (odd[0] == bufs[0]) ? scr[0] : bufs[0]; }
+    auto run_qap_ntt = [&]() -> int {
+        int my[3], m = 0;
+        for (int j = 0; j < 3; j++) if (owner(j) == rank) my[m++] = j;
+        if (m) {
+            // buildABC1 (:147-187)
+            { ProfScope pq(&c->stats, PROF_QAP, c->stream);
+              rc = fr_qap_rows(cv, k->d_rowptr, k->d_sig, k->d_coef, k->dW, k->dA_T, k->dB_T, k->dC_T, n, c->stream); c->launches++;
+              pq.end(); }
+            if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_qap_rows");
+            // :64-76  ifft -> batchApplyKey(1, inc) -> fft, with 1/n of the inverse folded into the coset table
+            const uint8_t* inc = (k->power == c->fr_s) ? c->shift.data() : c->roots[k->power + 1].data();
+            uint8_t ninv[32];
+            if (cv == SB_BN254) ninv_bytes<BnFr>(k->power, ninv); else ninv_bytes<BlsFr>(k->power, ninv);
+            FrPre pre; rc = get_pre(c, n, ninv, inc, &pre); if (rc) return rc;
+            // this rank's transforms run as one batch per pass (grids fill whole waves)
+            void* a[3]; void* b[3];
+            for (int i = 0; i < m; i++) { a[i] = bufs[my[i]]; b[i] = scr[my[i]]; }
+            FrNttTables tbi, tbf;
+            rc = get_ntt_tab(c, k->power, true, &tbi); if (rc) return rc;
+            rc = get_ntt_tab(c, k->power, false, &tbf); if (rc) return rc;
+            int side = 0, launches = 0;
+            ProfScope pn(&c->stats, PROF_NTT, c->stream);
+            rc = fr_ntt_batch(cv, a, b, m, k->power, &tbi, nullptr, nullptr, c->stream, &side, &launches);      // unscaled inverse
+            if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt_batch");
+            void** src = side ? b : a; void** dst = side ? a : b;
+            int side2 = 0;
+            rc = fr_ntt_batch(cv, src, dst, m, k->power, &tbf, &pre, nullptr, c->stream, &side2, &launches);     // coset NTT, 1/n folded in
+            if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt_batch");
+            pn.end();
+            c->launches += launches;
+            void** res = side2 ? dst : src;
+            for (int i = 0; i < m; i++) if (res[i] != odd[my[i]]) return fail(c, SB_ERR_CUDA, "internal: NTT result buffer mismatch");
+        }
+        if (dist && world > 1) {   // coset evaluations of chain j: owner -> every other rank's H range
+            NC(c, nc, nc->GroupStart());
+            for (int j = 0; j < 3; j++) {
+                const int o = owner(j);
+                if (o == rank) {
+                    for (int q = 0; q < world; q++) {
+                        if (q == rank) continue;
+                        uint64_t qlo, qcnt; range_of(n, q, qlo, qcnt);
+                        if (qcnt) NC(c, nc, nc->Send((const uint8_t*)odd[j] + qlo * 32, qcnt * 32, ncclUint8, q, c->comm, c->stream));
+                    }
+                } else if (hcnt) NC(c, nc, nc->Recv((uint8_t*)odd[j] + hlo * 32, hcnt * 32, ncclUint8, o, c->comm, c->stream));
+            }
+            NC(c, nc, nc->GroupEnd());
+        }
+        // joinABC (:320-374) -> plain scalars for the H MSM, over this rank's H range, into the remaining scratch buffer
+        if (hcnt) {
+            ProfScope pj(&c->stats, PROF_JOIN, c->stream);
+            rc = fr_join_abc(cv, (const uint8_t*)odd[0] + hlo * 32, (const uint8_t*)odd[1] + hlo * 32, (const uint8_t*)odd[2] + hlo * 32,
+                             (uint8_t*)tmp + hlo * 32, hcnt, c->stream); c->launches++;
+            pj.end();
+            if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_join_abc");
+        }
+        return 0;
+    };
     const GroupOps& G1 = c->g1; const GroupOps& G2 = c->g2;
     uint8_t* pA = partials; uint8_t* pB1 = pA + G1.xyzz_bytes; uint8_t* pC = pB1 + G1.xyzz_bytes; uint8_t* pH = pC + G1.xyzz_bytes; uint8_t* pB2 = pH + G1.xyzz_bytes;
     memset(partials, 0, 4 * G1.xyzz_bytes + G2.xyzz_bytes);
+    std::vector<uint8_t> sA(G1.xyzz_bytes, 0), rB1(G1.xyzz_bytes, 0);
     const uint64_t MAXC = 1ull << (g_msm_tuning[6] > 0 ? g_msm_tuning[6] : 23);   // points per MSM chunk (tuning key 6: test hook)
-    uint64_t wlo, wcnt; range(nv, wlo, wcnt);
-    uint64_t hlo, hcnt; range(n, hlo, hcnt);
     // a key loaded with sb_groth16_load_sharded only holds its own ranges: local indexing
     const bool local = k->n_shards > 1;
     if (local && (shard != k->shard || n_shards != k->n_shards)) return fail(c, SB_ERR_ARG, "proving key was loaded for a different shard");
     const uint64_t wb = local ? 0 : wlo, hb = local ? 0 : hlo;   // base-set index of this call's first point
-    if (wcnt <= MAXC && hcnt <= MAXC && wcnt > 0 && hcnt > 0 && c->pinned) {
+    const bool overlapped = wcnt <= MAXC && hcnt <= MAXC && wcnt > 0 && hcnt > 0 && c->pinned;
+    if (dist && world > 1 && !overlapped) return fail(c, SB_ERR_ARG, "distributed proving needs at least one point per rank and shards of at most 2^23 points");
+    if (overlapped) {
         // Overlapped pipeline: the witness is sorted once (A, B1, B2 and C all multiply it, :84-97); the four bucket
         // pipelines run on their own streams so that the latency-bound tails (fold cascade, bucket reduction) of one
         // MSM hide under the throughput-bound accumulation of the next; the H scalars (QAP/NTT chain) are produced
@@ -990,7 +1146,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         const bool serial = g_msm_tuning[2] != 0;
         cudaStream_t s0 = c->stream;
         // schedule: main stream  : H2D, sort(witness), acc B2, acc A, acc B1, acc C, [join NTT chain], acc H
-        //           aux[5] (hi)  : QAP -> iNTT -> coset NTT -> joinABC -> sort(H scalars)
+        //           aux[5] (hi)  : QAP -> iNTT -> coset NTT -> [exchange] -> joinABC -> sort(H scalars)
         //           aux[0..4](hi): the latency-bound tail of each MSM (fold, reduce, window sum, D2H)
         cudaStream_t sN = serial ? s0 : c->aux[5];
         MsmGeom gw = msm_geometry(wcnt, 32, c->fr_bits), gh = msm_geometry(hcnt, 32, c->fr_bits);
@@ -1010,19 +1166,16 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         c->stream = saved;
         if (rc) return rc;
         CU(c, cudaEventRecord(c->pev[1], sN));
-        static cudaEvent_t tl_ev[8]; static bool tl_init = false;
-        const bool tl = getenv("SB_TIMELINE") != nullptr;
-        if (tl && !tl_init) { for (auto& e : tl_ev) cudaEventCreate(&e); tl_init = true; }
-        if (tl) cudaEventRecord(tl_ev[5], sN);
         // witness MSMs on the main stream
         MsmSorted sw;
         rc = msm_sort_entries((const uint8_t*)k->dW + wlo * 32, 32, wcnt, gw, c->sort_scratch, s0, &sw, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
         tick(c, 2);
         struct Job { const GroupOps* G; const void* bases; size_t off; size_t len; uint8_t* dst; int tag; const MsmSorted* srt; const MsmGeom* g; };
-        Job jobs[5] = {{&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wb * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2, &sw, &gw},
-                       {&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wb * G1.aff_bytes), 0, w1, pA, SB_G1, &sw, &gw},
+        // order: A and B1 first (their results feed the host-side s*A + r*B1), then the long G2 MSM, C, and H last
+        Job jobs[5] = {{&G1, pre ? k->tA : (const void*)((const uint8_t*)k->dA + wb * G1.aff_bytes), 0, w1, pA, SB_G1, &sw, &gw},
                        {&G1, pre ? k->tB1 : (const void*)((const uint8_t*)k->dB1 + wb * G1.aff_bytes), w1, w1, pB1, SB_G1, &sw, &gw},
+                       {&G2, pre ? k->tB2 : (const void*)((const uint8_t*)k->dB2 + wb * G2.aff_bytes), 3 * w1, w2, pB2, SB_G2, &sw, &gw},
                        {&G1, pre ? k->tC : (const void*)((const uint8_t*)k->dC + wb * G1.aff_bytes), 2 * w1, w1, pC, SB_G1, &sw, &gw},
                        {&G1, pre ? k->tH : (const void*)((const uint8_t*)k->dH + hb * G1.aff_bytes), 3 * w1 + w2, wh, pH, SB_G1, &sh, &gh}};
         for (int i = 0; i < 5; i++) {
@@ -1035,22 +1188,14 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
             if (i == 0) CU(c, cudaMemcpyAsync(&hcounts[0], sw.counts, 8, cudaMemcpyDeviceToHost, st));
             if (i == 4) CU(c, cudaMemcpyAsync(&hcounts[1], sh.counts, 8, cudaMemcpyDeviceToHost, st));
             CU(c, cudaEventRecord(c->pev[2 + i], st));
-            if (tl) cudaEventRecord(tl_ev[i], st);
         }
         tick(c, 3);
         // host recombination as each MSM lands (overlaps with the MSMs still running)
         for (int i = 0; i < 5; i++) {
             CU(c, cudaEventSynchronize(c->pev[2 + i]));
             jobs[i].G->combine(hws + jobs[i].off, *jobs[i].g, jobs[i].dst);
-        }
-        if (tl) {
-            cudaDeviceSynchronize();
-            float t; cudaEventElapsedTime(&t, c->ev[0], tl_ev[5]); fprintf(stderr, "[timeline] ntt chain + sort H done at %.3f ms\n", t);
-            for (int i = 0; i + 1 < c->stats.used; i += 2) {
-                float a, b; cudaEventElapsedTime(&a, c->ev[0], c->prof_ev[i]); cudaEventElapsedTime(&b, c->ev[0], c->prof_ev[i + 1]);
-                float e; cudaEventElapsedTime(&e, c->ev[0], tl_ev[i / 2]);
-                fprintf(stderr, "[timeline] msm %d: accumulate %.3f -> %.3f ms, tail done %.3f ms\n", i / 2, a, b, e);
-            }
+            if (ps && i == 0) G1.times(pA, ps->sp, 32, sA.data());      // s * A   (src/groth16_prove.js:117: pi_c += s*pi_a)
+            if (ps && i == 1) G1.times(pB1, ps->rp, 32, rB1.data());    // r * B1  (:118)
         }
         // join the side streams back into the main stream
         if (!serial) { for (int i = 0; i < 5; i++) CU(c, cudaStreamWaitEvent(s0, c->pev[2 + i], 0)); CU(c, cudaStreamWaitEvent(s0, c->pev[1], 0)); }
@@ -1086,6 +1231,11 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         rc = msm_dev_accumulate(c, G1, (const uint8_t*)k->dH + hb * G1.aff_bytes, (const uint8_t*)tmp + hlo * 32, 32, hcnt, pH);
         if (rc) return rc;
     }
+    if (ps) { G1.times(pA, ps->sp, 32, sA.data()); G1.times(pB1, ps->rp, 32, rB1.data()); }
+    }
+    if (ps) {   // C' = C + H + s*A + r*B1;  the B1 and H slots are spent
+        G1.add(pC, pH); G1.add(pC, sA.data()); G1.add(pC, rB1.data());
+        memset(pB1, 0, G1.xyzz_bytes); memset(pH, 0, G1.xyzz_bytes);
     }
     tick(c, 4);
     cudaEventSynchronize(c->ev[4]);
@@ -1097,6 +1247,18 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
 // host part: proof assembly, src/groth16_prove.js:103-132
 
 struct VkPoints { const uint8_t *alpha1, *beta1, *beta2, *delta1, *delta2; };
+static void plain_scalars(int curve, const uint8_t r[32], const uint8_t s[32], uint8_t rp[32], uint8_t sp[32], uint8_t rsp[32], bool negate_rs) {
+    uint8_t rs[32];
+    if (curve == SB_BN254) {
+        fr_from_mont_bytes<BnFr>(r, rp); fr_from_mont_bytes<BnFr>(s, sp);
+        Fp<BnFr> a, b; memcpy(&a, r, 32); memcpy(&b, s, 32); a = Fp<BnFr>::mul(a, b); if (negate_rs) a = Fp<BnFr>::neg(a); memcpy(rs, &a, 32);
+        fr_from_mont_bytes<BnFr>(rs, rsp);
+    } else {
+        fr_from_mont_bytes<BlsFr>(r, rp); fr_from_mont_bytes<BlsFr>(s, sp);
+        Fp<BlsFr> a, b; memcpy(&a, r, 32); memcpy(&b, s, 32); a = Fp<BlsFr>::mul(a, b); if (negate_rs) a = Fp<BlsFr>::neg(a); memcpy(rs, &a, 32);
+        fr_from_mont_bytes<BlsFr>(rs, rsp);
+    }
+}
 static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& G2, const VkPoints& vk, const uint8_t* partials,
                                  const uint8_t r[32], const uint8_t s[32], uint8_t* proof);
 static int groth16_assemble(sb_ctx* c, Groth16Key* k, const uint8_t* partials, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
@@ -1108,9 +1270,8 @@ static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& 
     const uint32_t x1 = G1.xyzz_bytes, x2 = G2.xyzz_bytes;
     std::vector<uint8_t> A(partials, partials + x1), B1(partials + x1, partials + 2 * x1), C(partials + 2 * x1, partials + 3 * x1),
         H(partials + 3 * x1, partials + 4 * x1), B2(partials + 4 * x1, partials + 4 * x1 + x2);
-    uint8_t rp[32], sp[32], rs[32], rsp[32];
-    if (curve == SB_BN254) { fr_from_mont_bytes<BnFr>(r, rp); fr_from_mont_bytes<BnFr>(s, sp); fr_neg_mul_bytes<BnFr>(r, s, rs); fr_from_mont_bytes<BnFr>(rs, rsp); }
-    else { fr_from_mont_bytes<BlsFr>(r, rp); fr_from_mont_bytes<BlsFr>(s, sp); fr_neg_mul_bytes<BlsFr>(r, s, rs); fr_from_mont_bytes<BlsFr>(rs, rsp); }
+    uint8_t rp[32], sp[32], rsp[32];
+    plain_scalars(curve, r, s, rp, sp, rsp, true);
     std::vector<uint8_t> t1(x1), t2(x2), d1(x1), d2(x2), pt(x1), pt2(x2);
     G1.from_affine(vk.delta1, d1.data()); G2.from_affine(vk.delta2, d2.data());
     // pi_a = A + alpha1 + r*delta1
@@ -1133,18 +1294,61 @@ static int groth16_assemble_host(int curve, const GroupOps& G1, const GroupOps& 
     return 0;
 }
 
+// The same assembly split so that nothing but three additions and three normalisations follows the last MSM:
+//   pi_a = A + [alpha1 + r*delta1],  pi_b = B2 + [beta2 + s*delta2],
+//   pi_c = C + H + s*pi_a + r*pib1 - rs*delta1 = [C + H + s*A + r*B1] + [s*alpha1 + r*beta1 + rs*delta1]
+// The bracketed fixed parts depend only on the key and (r, s): a helper thread computes them while the GPU works;
+// the C bracket is folded by groth16_device (ProofScalars) as A and B1 land.  Same group elements, same proof bytes.
+struct FixedParts { std::vector<uint8_t> Fa, Fb, Fc; };
+static FixedParts groth16_fixed_parts(int curve, const GroupOps& G1, const GroupOps& G2, const VkPoints vk, const uint8_t* r, const uint8_t* s) {
+    const uint32_t x1 = G1.xyzz_bytes, x2 = G2.xyzz_bytes;
+    uint8_t rp[32], sp[32], rsp[32];
+    plain_scalars(curve, r, s, rp, sp, rsp, false);
+    FixedParts f; f.Fa.assign(x1, 0); f.Fb.assign(x2, 0); f.Fc.assign(x1, 0);
+    std::vector<uint8_t> a1(x1), b1(x1), d1(x1), b2(x2), d2(x2), t1(x1), t2(x2);
+    G1.from_affine(vk.alpha1, a1.data()); G1.from_affine(vk.beta1, b1.data()); G1.from_affine(vk.delta1, d1.data());
+    G2.from_affine(vk.beta2, b2.data()); G2.from_affine(vk.delta2, d2.data());
+    std::future<void> g2 = std::async(std::launch::async, [&]() { G2.times(d2.data(), sp, 32, t2.data()); });   // the one G2 multiple, on its own thread
+    G1.times(d1.data(), rp, 32, t1.data()); f.Fa = a1; G1.add(f.Fa.data(), t1.data());
+    G1.times(a1.data(), sp, 32, f.Fc.data());
+    G1.times(b1.data(), rp, 32, t1.data()); G1.add(f.Fc.data(), t1.data());
+    G1.times(d1.data(), rsp, 32, t1.data()); G1.add(f.Fc.data(), t1.data());
+    g2.get();
+    f.Fb = b2; G2.add(f.Fb.data(), t2.data());
+    return f;
+}
+static void groth16_finish_folded(const GroupOps& G1, const GroupOps& G2, const FixedParts& f, const uint8_t* partials, uint8_t* proof) {
+    const uint32_t x1 = G1.xyzz_bytes, x2 = G2.xyzz_bytes;
+    std::vector<uint8_t> A(partials, partials + x1), C(partials + 2 * x1, partials + 3 * x1), B2(partials + 4 * x1, partials + 4 * x1 + x2);
+    G1.add(A.data(), f.Fa.data()); G2.add(B2.data(), f.Fb.data()); G1.add(C.data(), f.Fc.data());
+    G1.to_affine(A.data(), proof);
+    G2.to_affine(B2.data(), proof + G1.aff_bytes);
+    G1.to_affine(C.data(), proof + G1.aff_bytes + G2.aff_bytes);
+}
+static int groth16_prove_folded(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) {
+    VkPoints vk{k->alpha1.data(), k->beta1.data(), k->beta2.data(), k->delta1.data(), k->delta2.data()};
+    const int curve = c->curve; const GroupOps G1 = c->g1, G2 = c->g2;
+    std::future<FixedParts> fixed = std::async(std::launch::async, [=]() { return groth16_fixed_parts(curve, G1, G2, vk, r, s); });
+    ProofScalars ps; uint8_t rsp[32]; plain_scalars(curve, r, s, ps.rp, ps.sp, rsp, false);
+    std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
+    int rc = groth16_device(c, k, witness, n_witness, 0, 1, partials.data(), &ps, false);
+    FixedParts f = fixed.get();
+    if (rc) return rc;
+    groth16_finish_folded(c->g1, c->g2, f, partials.data(), proof);
+    return 0;
+}
+
 int sb_groth16_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
     if (k->n_shards > 1) return fail(c, SB_ERR_ARG, "proving key was loaded sharded: use sb_groth16_prove_shard + sb_groth16_finish");
-    std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
-    int rc = groth16_device(c, k, witness, n_witness, 0, 1, partials.data()); if (rc) return rc;
-    return groth16_assemble(c, k, partials.data(), r, s, proof);
+    if (!witness || !r || !s || !proof) return fail(c, SB_ERR_ARG, "null argument");
+    return groth16_prove_folded(c, k, witness, n_witness, r, s, proof);
 }
 int sb_groth16_prove_resident(sb_ctx* c, uint64_t h, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
-    std::vector<uint8_t> partials(sb_groth16_partials_bytes(c));
-    int rc = groth16_device(c, k, nullptr, k->nVars, 0, 1, partials.data()); if (rc) return rc;
-    return groth16_assemble(c, k, partials.data(), r, s, proof);
+    if (k->n_shards > 1) return fail(c, SB_ERR_ARG, "proving key was loaded sharded: use sb_groth16_prove_shard + sb_groth16_finish");
+    if (!r || !s || !proof) return fail(c, SB_ERR_ARG, "null argument");
+    return groth16_prove_folded(c, k, nullptr, k->nVars, r, s, proof);
 }
 int sb_groth16_prove_shard(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, int shard, int n_shards, uint8_t* partials_out) { SB_LOCK(c);
     Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
@@ -1162,6 +1366,80 @@ int sb_groth16_finish(sb_ctx* c, uint64_t h, const uint8_t* all, int n_shards, c
         G2.add(acc.data() + 4 * x1, p + 4 * x1);
     }
     return groth16_assemble(c, k, acc.data(), r, s, proof);
+}
+
+// One proof across the ranks of a communicator (collective: every rank calls it with the same witness, r and s).
+// witness may be null on every rank to reuse the resident one.  proof_affine_out may be null on ranks that do not need
+// the proof; ranks that pass a buffer all receive the same bytes.
+int sb_groth16_prove_dist(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_witness, const uint8_t r[32], const uint8_t s[32], uint8_t* proof) { SB_LOCK(c);
+    Groth16Key* k = get_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid groth16 handle");
+    if (!c->comm) return fail(c, SB_ERR_ARG, "context has no communicator: call sb_comm_init_rank first");
+    if (!r || !s) return fail(c, SB_ERR_ARG, "null argument");
+    NcclApi* nc = nccl_api(nullptr);
+    VkPoints vk{k->alpha1.data(), k->beta1.data(), k->beta2.data(), k->delta1.data(), k->delta2.data()};
+    const int curve = c->curve; const GroupOps G1 = c->g1, G2 = c->g2;
+    std::future<FixedParts> fixed;
+    if (proof) fixed = std::async(std::launch::async, [=]() { return groth16_fixed_parts(curve, G1, G2, vk, r, s); });
+    ProofScalars ps; uint8_t rsp[32]; plain_scalars(curve, r, s, ps.rp, ps.sp, rsp, false);
+    const size_t pb = sb_groth16_partials_bytes(c);
+    uint8_t* mine = c->h_xchg + pb * c->world;
+    int rc = groth16_device(c, k, witness, n_witness, c->rank, c->world, mine, &ps, true);
+    if (rc) { if (proof) fixed.get(); return rc; }
+    cudaError_t e = cudaMemcpyAsync((uint8_t*)c->d_xchg + pb * c->rank, mine, pb, cudaMemcpyHostToDevice, c->stream);
+    ncclResult_t nr = ncclSuccess;
+    if (e == cudaSuccess) nr = nc->AllGather((const uint8_t*)c->d_xchg + pb * c->rank, c->d_xchg, pb, ncclUint8, c->comm, c->stream);
+    if (e == cudaSuccess && nr == ncclSuccess && proof) e = cudaMemcpyAsync(c->h_xchg, c->d_xchg, pb * c->world, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (proof) {
+        FixedParts f = fixed.get();
+        if (e == cudaSuccess && nr == ncclSuccess) {
+            const uint32_t x1 = G1.xyzz_bytes;
+            std::vector<uint8_t> acc(pb, 0);
+            for (int i = 0; i < c->world; i++) {
+                const uint8_t* p = c->h_xchg + (size_t)i * pb;
+                G1.add(acc.data(), p); G1.add(acc.data() + 2 * x1, p + 2 * x1); G2.add(acc.data() + 4 * x1, p + 4 * x1);
+            }
+            groth16_finish_folded(G1, G2, f, acc.data(), proof);
+        }
+    }
+    if (nr != ncclSuccess) return fail(c, SB_ERR_CUDA, std::string("ncclAllGather: ") + nc->GetErrorString(nr));
+    if (e != cudaSuccess) return cuda_fail(c, e, "partial exchange");
+    return 0;
+}
+
+// ---- single-process multi-GPU convenience (what a Node addon calls): one context per device, one host thread per
+// context inside each call.  SURVEY §8b: sb_create(curve, device_ids, n_devices) with the communicator built here.
+int sb_create_multi(int curve, const int* device_ids, int n_devices, sb_ctx** out) {
+    if (!device_ids || !out || n_devices < 1 || n_devices > 64) return SB_ERR_ARG;
+    for (int i = 0; i < n_devices; i++) out[i] = nullptr;
+    int rc = 0;
+    for (int i = 0; i < n_devices && !rc; i++) rc = sb_create(curve, device_ids[i], &out[i]);
+    uint8_t id[128];
+    if (!rc && n_devices > 1) rc = sb_comm_unique_id(id);
+    if (!rc && n_devices > 1) {
+        std::vector<std::future<int>> f;
+        for (int i = 0; i < n_devices; i++) f.push_back(std::async(std::launch::async, [=]() { return sb_comm_init_rank(out[i], n_devices, i, id); }));
+        for (auto& x : f) { int r = x.get(); if (r && !rc) rc = r; }
+    }
+    if (rc) { for (int i = 0; i < n_devices; i++) { if (out[i]) sb_destroy(out[i]); out[i] = nullptr; } }
+    return rc;
+}
+int sb_groth16_load_multi(sb_ctx* const* ctxs, int n, const uint8_t* zkey, uint64_t zkey_len, uint64_t* handles) {
+    if (!ctxs || !zkey || !handles || n < 1) return SB_ERR_ARG;
+    std::vector<std::future<int>> f;
+    for (int i = 0; i < n; i++) f.push_back(std::async(std::launch::async, [=]() { return sb_groth16_load_sharded(ctxs[i], zkey, zkey_len, i, n, &handles[i]); }));
+    int rc = 0; for (auto& x : f) { int r = x.get(); if (r && !rc) rc = r; }
+    return rc;
+}
+int sb_groth16_prove_multi(sb_ctx* const* ctxs, const uint64_t* handles, int n, const uint8_t* witness, uint64_t n_witness,
+                           const uint8_t r[32], const uint8_t s[32], uint8_t* proof_affine_out) {
+    if (!ctxs || !handles || n < 1 || !proof_affine_out) return SB_ERR_ARG;
+    if (n == 1) return sb_groth16_prove(ctxs[0], handles[0], witness, n_witness, r, s, proof_affine_out);
+    std::vector<std::future<int>> f;
+    for (int i = 0; i < n; i++)
+        f.push_back(std::async(std::launch::async, [=]() { return sb_groth16_prove_dist(ctxs[i], handles[i], witness, n_witness, r, s, i == 0 ? proof_affine_out : nullptr); }));
+    int rc = 0; for (auto& x : f) { int r2 = x.get(); if (r2 && !rc) rc = r2; }
+    return rc;
 }
 
 // ---- host-only helpers (no context, no device): the combine/assembly half of the multi-GPU path, testable on CPU

@@ -30,6 +30,7 @@ int fr_ntt_batch(int curve, void* const* a, void* const* b, int count, int L, co
         return (int)cudaGetLastError();
     })
 }
+int fr_ntt_passes(int L) { return ntt_plan(L).npass; }
 int fr_apply_key(int curve, const void* in, void* out, uint64_t n, const FrPre* t, cudaStream_t stream) {
     FR_DISPATCH(curve, {
         NttPre<F> p; p.lo = (const F*)t->lo; p.hi = (const F*)t->hi; p.h = t->h;

@@ -408,8 +408,18 @@ extern int g_msm_tuning[8];
 
 struct MsmLaunchStats {
     int launches = 0;
-    // optional profiling: event pairs recorded around each k_accumulate launch (tag = group id)
+    // optional profiling: event pairs recorded around kernel groups (tag = PROF_* below; accumulation uses cur_tag)
     cudaEvent_t* ev = nullptr; int nev = 0; int used = 0; int tag[32] = {0}; int cur_tag = 0;
+};
+enum { PROF_ACC_G1 = 1, PROF_ACC_G2 = 2, PROF_SORT = 3, PROF_FOLD = 4, PROF_REDUCE = 5, PROF_QAP = 6, PROF_NTT = 7, PROF_JOIN = 8 };
+// one event pair around a group of launches on `st`; a no-op unless profiling is armed (api.cu prof_begin)
+struct ProfScope {
+    MsmLaunchStats* s; cudaStream_t st; int idx = -1;
+    ProfScope(MsmLaunchStats* s_, int tag, cudaStream_t st_) : s(s_), st(st_) {
+        if (s && s->ev && s->used + 2 <= s->nev && s->used / 2 < 32) { idx = s->used; s->used += 2; s->tag[idx / 2] = tag; cudaEventRecord(s->ev[idx], st); }
+    }
+    void end() { if (idx >= 0) { cudaEventRecord(s->ev[idx + 1], st); idx = -1; } }
+    void end(cudaStream_t other) { st = other; end(); }
 };
 
 // Sorted digit entries of one scalar vector; shared by every MSM that uses the same scalars
@@ -481,8 +491,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     uint32_t* K[2] = {(uint32_t*)(base + o_KA), (uint32_t*)(base + o_KB)};
     F* Ls = (F*)(base + o_L);
     int launches = 0;
-    const bool prof = stats && stats->ev && stats->used + 2 <= stats->nev && stats->used / 2 < 32;
-    if (prof) cudaEventRecord(stats->ev[stats->used], stream);
+    ProfScope prof(stats, stats ? stats->cur_tag : 0, stream);
     int rc = msm_pair_offsets(s.keys, s.counts, NB, offA, stream); launches++;
     if (rc) return rc;
     const Affine<F>* src = d_bases; uint32_t* in = offA; uint32_t* out = offB;
@@ -501,7 +510,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     rc = msm_pair_counts(in, NB, counts2, stream); launches++;
     if (rc) return rc;
     s2.counts = counts2;
-    if (prof) { cudaEventRecord(stats->ev[stats->used + 1], stream); stats->tag[stats->used / 2] = stats->cur_tag; stats->used += 2; }
+    prof.end();
     if (stats) stats->launches += launches;
     // the segmented pipeline on the reduced list; its own accumulate launch is not separately profiled (nev guard)
     cudaEvent_t* sev = stats ? stats->ev : nullptr; if (stats) stats->ev = nullptr;
@@ -540,8 +549,7 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
     int launches = 0;
     cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), stream);
     if (heads0) {
-        const bool prof = stats && stats->ev && stats->used + 2 <= stats->nev && stats->used / 2 < 32;
-        if (prof) cudaEventRecord(stats->ev[stats->used], stream);
+        ProfScope prof(stats, stats ? stats->cur_tag : 0, stream);
         {
             const unsigned grid = (unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
             // occupancy variants (sb_set_tuning(0, minBlocksPerSM)): base-field groups run best at 4 CTAs/SM (124 regs);
@@ -558,10 +566,11 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
             }
             launches++;
         }
-        if (prof) { cudaEventRecord(stats->ev[stats->used + 1], stream); stats->tag[stats->used / 2] = stats->cur_tag; stats->used += 2; }
+        prof.end();
         if (tail_stream && tail_stream != stream && ev_acc) {
             cudaEventRecord(ev_acc, stream); cudaStreamWaitEvent(tail_stream, ev_acc, 0); stream = tail_stream;
         }
+        ProfScope pfold(stats, PROF_FOLD, stream);
         k_fold_short<F><<<(unsigned)((heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
             headsA, hkA, hkM, s.counts, buckets); launches++;
         // fold cascade: level l consumes counts[l] heads (upper bound m on the host, exact count on the device)
@@ -576,8 +585,10 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
             XYZZ<F>* th = hin; hin = hout; hout = th; uint32_t* tk = kin; kin = kout; kout = tk;
             if (level >= 8) return (int)cudaErrorUnknown;
         }
+        pfold.end();
     }
     if (!heads0 && tail_stream && tail_stream != stream && ev_acc) { cudaEventRecord(ev_acc, stream); cudaStreamWaitEvent(tail_stream, ev_acc, 0); stream = tail_stream; }
+    ProfScope pred(stats, PROF_REDUCE, stream);
     if (g.B >= (uint32_t)RED2_BUCKETS && g.B / RED2_BUCKETS <= 1024 && g_msm_tuning[1] == 2) {   // experimental: less work (-36 %) but 2-3x the
         // dependent-add latency of k_reduce; measured slower (proof 27.4 ms vs 26.0 ms overlapped, 31.3 vs 26.6 serialised)
         // hierarchical reduction: per-CTA (R, S) pairs live in the partials area (2 * NC entries per window <= ctas_per_window)
@@ -595,6 +606,7 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
         k_reduce<F><<<NW * ctas_per_window, red_threads, red_threads * sizeof(XYZZ<F>), stream>>>(buckets, g, partials, ctas_per_window); launches++;
         k_window_sum<F><<<NW, 32, 32 * sizeof(XYZZ<F>), stream>>>(partials, ctas_per_window, d_wsum); launches++;
     }
+    pred.end();
     if (stats) stats->launches += launches;
     return (int)cudaGetLastError();
 }

@@ -117,12 +117,14 @@ int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmG
     uint32_t* vals0 = (uint32_t*)(base + o_vals0); uint32_t* vals1 = (uint32_t*)(base + o_vals1);
     uint64_t* counts = (uint64_t*)(base + o_counts);
     int launches = 0;
+    ProfScope prof(stats, PROF_SORT, stream);
     k_digits<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_scalars, sbytes, n, g, keys0, vals0); launches++;
     kb = cub::DoubleBuffer<uint32_t>(keys0, keys1); vb = cub::DoubleBuffer<uint32_t>(vals0, vals1);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, kb, vb, (uint64_t)total, 0, end_bit, stream);
     if (e != cudaSuccess) return (int)e;
     launches += 2 + (end_bit + 7) / 8;   // histogram + scan + one onesweep pass per 8 key bits
     k_count_valid<<<1, 1, 0, stream>>>(kb.Current(), total, counts); launches++;
+    prof.end();
     out->keys = kb.Current(); out->vals = vb.Current(); out->counts = counts; out->n = n; out->total = total; out->g = g;
     if (stats) stats->launches += launches;
     return (int)cudaGetLastError();

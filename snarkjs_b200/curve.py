@@ -192,6 +192,18 @@ class Curve:
     def last_ms(self, which=0) -> float:
         return float(self._ctx.lib.sb_last_ms(self._ctx.h, which))
 
+    # ---- multi-GPU: one NCCL rank per context (include/snarkb200.h, sb_comm_*)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        out = np.zeros(128, np.uint8)
+        if N.lib().sb_comm_unique_id(_ptr(out)) != 0:
+            raise SbError("sb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return out.tobytes()
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        idb = np.frombuffer(bytes(unique_id), np.uint8)
+        self.check(self.lib.sb_comm_init_rank(self.handle, world, rank, _ptr(idb)))
+
     def terminate(self):
         self._ctx.close()
 

@@ -181,6 +181,16 @@ class ProvingKey:
         self.curve.check(self.curve.lib.sb_groth16_finish(self.curve.handle, self.handle, _ptr(p), n_shards, bytes(r), bytes(s), _ptr(out)))
         return out.tobytes()
 
+    def prove_dist(self, witness, r: bytes, s: bytes, want_proof: bool = True):
+        """One proof across the ranks of the curve's communicator (Curve.comm_init): a collective call.  The key must be
+        this rank's shard (ProvingKey(..., shard=rank, n_shards=world)).  witness=None reuses the resident witness."""
+        w = None if witness is None else _arr(witness)
+        out = np.empty(8 * self.curve.n8q, np.uint8) if want_proof else None
+        self.curve.check(self.curve.lib.sb_groth16_prove_dist(self.curve.handle, self.handle, None if w is None else _ptr(w),
+                                                               self.nVars if w is None else w.size // 32, bytes(r), bytes(s),
+                                                               None if out is None else _ptr(out)))
+        return None if out is None else out.tobytes()
+
     def release(self):
         if self.handle:
             self.curve.lib.sb_groth16_release(self.curve.handle, self.handle)

@@ -81,3 +81,16 @@ def test_prover_entry_points_reject_null_context():
         assert release(None, 1) == -1
     assert L.sb_plonk_proof_bytes(None) == 0 and L.sb_fflonk_proof_bytes(None) == 0
     assert L.sb_plonk_info(None, 1, None, None, None, None) == -1 and L.sb_fflonk_info(None, 1, None, None, None, None) == -1
+
+
+def test_dist_entry_points_without_gpu():
+    """Chain placement is a pure function; the communicator entry points refuse null contexts; asking for a unique id
+    loads libnccl.so.2 lazily (present in this image) without touching a device."""
+    L = N.lib()
+    assert [L.sb_dist_chain_owner(j, 1) for j in range(3)] == [0, 0, 0]
+    assert [L.sb_dist_chain_owner(j, 2) for j in range(3)] == [0, 1, 0]
+    assert [L.sb_dist_chain_owner(j, 8) for j in range(3)] == [0, 1, 2]
+    idb = np.zeros(128, np.uint8)
+    assert L.sb_comm_init_rank(None, 2, 0, idb.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert L.sb_groth16_prove_dist(None, 1, None, 0, None, None, None) == -1
+    assert L.sb_comm_info(None, None, None) == -1
