@@ -39,10 +39,11 @@ def parse():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="groth16", choices=["groth16", "plonk", "fflonk"])
-    ap.add_argument("--curve", default="bn128", choices=["bn128", "bls12381"])
+    ap.add_argument("--curve", default=None, choices=["bn128", "bls12381"], help="default: bn128 (groth16, fflonk), bls12381 (plonk: BASELINE config #5)")
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 domain of the CPU arm's sample (0 = the full workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--witness-like", action="store_true", help="witness distribution of real circuits (SURVEY 8d): 50%% zeros, 25%% ones, 25%% uniform")
+    ap.add_argument("--tune", action="append", default=[], help="experimental kernel-variant switch k=v (sb_set_tuning), e.g. 1=1 = legacy bucket reduction")
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"], help="N > 1: which number is `value` (the other one is reported beside it)")
     return ap.parse_args()
 
@@ -194,6 +195,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     L = args.log_n
     curve = snarkjs_b200.getCurveFromName("bn128", device=local)
+    for kv in args.tune:
+        k_, v_ = kv.split("=")
+        curve.lib.sb_set_tuning(int(k_), int(v_))
     peak_modmul = curve.lib.sb_calibrate(curve.handle, 1) if rank == 0 else 0.0
     peak_imad = curve.lib.sb_calibrate(curve.handle, 0) if rank == 0 else 0.0
     t0 = time.perf_counter()

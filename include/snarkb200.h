@@ -115,6 +115,9 @@ int sb_plonk_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t*
 int sb_plonk_load_file(sb_ctx* ctx, const char* zkey_path, uint64_t* handle);
 int sb_plonk_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions);
 uint32_t sb_plonk_proof_bytes(sb_ctx* ctx);
+/* the same proof from the witness the previous sb_plonk_prove on this key left in HBM (device-resident timing, and
+ * re-proving with fresh blinders without a second upload) */
+int sb_plonk_prove_resident(sb_ctx* ctx, uint64_t handle, const uint8_t* blinders, uint8_t* proof_out);
 int sb_plonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,
                    uint8_t* proof_out);
 int sb_plonk_release(sb_ctx* ctx, uint64_t handle);
@@ -129,6 +132,7 @@ int sb_fflonk_load(sb_ctx* ctx, const uint8_t* zkey, uint64_t zkey_len, uint64_t
 int sb_fflonk_load_file(sb_ctx* ctx, const char* zkey_path, uint64_t* handle);
 int sb_fflonk_info(sb_ctx* ctx, uint64_t handle, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size, uint32_t* n_additions);
 uint32_t sb_fflonk_proof_bytes(sb_ctx* ctx);
+int sb_fflonk_prove_resident(sb_ctx* ctx, uint64_t handle, const uint8_t* blinders, uint8_t* proof_out);
 int sb_fflonk_prove(sb_ctx* ctx, uint64_t handle, const uint8_t* witness, uint64_t n_witness, const uint8_t* blinders,
                     uint8_t* proof_out);
 int sb_fflonk_release(sb_ctx* ctx, uint64_t handle);

@@ -51,12 +51,14 @@ _SIGNATURES = {
     "sb_plonk_info": (ctypes.c_int, [vp, u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "sb_plonk_proof_bytes": (u32, [vp]),
     "sb_plonk_prove": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_char_p, vp]),
+    "sb_plonk_prove_resident": (ctypes.c_int, [vp, u64, ctypes.c_char_p, vp]),
     "sb_plonk_release": (ctypes.c_int, [vp, u64]),
     "sb_fflonk_load": (ctypes.c_int, [vp, vp, u64, ctypes.POINTER(u64)]),
     "sb_fflonk_load_file": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.POINTER(u64)]),
     "sb_fflonk_info": (ctypes.c_int, [vp, u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "sb_fflonk_proof_bytes": (u32, [vp]),
     "sb_fflonk_prove": (ctypes.c_int, [vp, u64, vp, u64, ctypes.c_char_p, vp]),
+    "sb_fflonk_prove_resident": (ctypes.c_int, [vp, u64, ctypes.c_char_p, vp]),
     "sb_fflonk_release": (ctypes.c_int, [vp, u64]),
     "sb_groth16_prove_resident": (ctypes.c_int, [vp, u64, vp, vp, vp]),
     "sb_last_stat": (ctypes.c_double, [vp, ctypes.c_int]),

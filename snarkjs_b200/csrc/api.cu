@@ -114,7 +114,7 @@ struct sb_ctx {
     std::vector<std::vector<uint8_t>> roots;   // w[0..s] Montgomery bytes
     std::vector<uint8_t> nqr, shift;
     std::vector<uint8_t> gen1, gen2;            // affine generators, Montgomery
-    cudaEvent_t prof_ev[64];
+    cudaEvent_t prof_ev[256];
     double stat[16] = {0};                       // see sb_last_stat
     // multi-GPU (sb_comm_init_rank): one NCCL rank per context
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
@@ -338,7 +338,7 @@ void init_generators(sb_ctx* c) {
 }
 
 // profiling helpers: accumulate-kernel event pairs
-void prof_begin(sb_ctx* c) { c->stats.ev = c->prof_ev; c->stats.nev = 64; c->stats.used = 0; for (double& d : c->stat) d = 0; }
+void prof_begin(sb_ctx* c) { c->stats.ev = c->prof_ev; c->stats.nev = 256; c->stats.used = 0; for (double& d : c->stat) d = 0; }
 void prof_end(sb_ctx* c) {
     for (int i = 0; i + 1 < c->stats.used; i += 2) {
         float ms = 0; if (cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -624,7 +624,9 @@ static int ntt_dev(sb_ctx* c, void* a, void* b, uint64_t n, int inverse, const F
     const void* post = nullptr;
     if (inverse && scale) { post = get_ninv(c, L); if (!post) return fail(c, SB_ERR_NOMEM, "out of device memory"); }
     int launches = 0;
+    ProfScope pn(&c->stats, PROF_NTT, c->stream);
     rc = fr_ntt(c->curve, a, b, L, &tb, pre, post, c->stream, result, &launches);
+    pn.end();
     c->launches += launches;
     if (rc) return cuda_fail(c, (cudaError_t)rc, "fr_ntt");
     return 0;
@@ -1547,6 +1549,14 @@ int sb_plonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_wit
     return c->curve == SB_BN254 ? plonk_prove_impl<BnFq, BnFr>(c, k, witness, n_witness, blinders, proof)
                                 : plonk_prove_impl<BlsFq, BlsFr>(c, k, witness, n_witness, blinders, proof);
 }
+int sb_plonk_prove_resident(sb_ctx* c, uint64_t h, const uint8_t* blinders, uint8_t* proof) { SB_LOCK(c);
+    PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
+    if (!blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
+    if (!k->n_wit_resident) return fail(c, SB_ERR_ARG, "no witness resident for this proving key: call sb_plonk_prove first");
+    cudaSetDevice(c->device);
+    return c->curve == SB_BN254 ? plonk_prove_impl<BnFq, BnFr>(c, k, nullptr, 0, blinders, proof)
+                                : plonk_prove_impl<BlsFq, BlsFr>(c, k, nullptr, 0, blinders, proof);
+}
 int sb_plonk_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
     PlonkKeyDev* k = get_plonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid plonk handle");
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
@@ -1574,6 +1584,13 @@ int sb_fflonk_prove(sb_ctx* c, uint64_t h, const uint8_t* witness, uint64_t n_wi
     if (!witness || !blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
     cudaSetDevice(c->device);
     return fflonk_prove_impl<BnFq, BnFr>(c, k, witness, n_witness, blinders, proof);
+}
+int sb_fflonk_prove_resident(sb_ctx* c, uint64_t h, const uint8_t* blinders, uint8_t* proof) { SB_LOCK(c);
+    FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");
+    if (!blinders || !proof) return fail(c, SB_ERR_ARG, "null argument");
+    if (!k->n_wit_resident) return fail(c, SB_ERR_ARG, "no witness resident for this proving key: call sb_fflonk_prove first");
+    cudaSetDevice(c->device);
+    return fflonk_prove_impl<BnFq, BnFr>(c, k, nullptr, 0, blinders, proof);
 }
 int sb_fflonk_release(sb_ctx* c, uint64_t h) { SB_LOCK(c);
     FflonkKeyDev* k = get_fflonk_key(c, h); if (!k) return fail(c, SB_ERR_ARG, "invalid fflonk handle");

@@ -26,6 +26,7 @@ struct FflonkKeyDev {
     void* d_cub = nullptr; size_t cub_bytes = 0;
     int* d_flag = nullptr; void* d_red = nullptr;
     bool c0_is_interleave = false;
+    std::vector<uint8_t> host_pub; uint64_t n_wit_resident = 0;   // as in PlonkKeyDev
     void* commit_scratch() const { return work[31]; }   // FflonkWork::scal
 };
 
@@ -210,10 +211,16 @@ template <class PQ, class PR> int fflonk_prove_impl(sb_ctx* c, FflonkKeyDev* kd,
     }
     CudaFflonkBackend<F> be; be.c = c; be.key = kd;
     std::string err;
+    const size_t pub_bytes = ((size_t)z.nPublic + 1) * 32;
+    if (!witness) { witness = kd->host_pub.data(); n_witness = kd->n_wit_resident; be.resident_dst = w.W; }
+    else { kd->n_wit_resident = 0; if (n_witness > z.nPublic) kd->host_pub.assign(witness, witness + pub_bytes); }
     tick(c, 0);
+    prof_begin(c);
     int rc = fflonk_prove_flow<PQ, PR>(be, k, w, witness, n_witness, blinders, proof, err);
     tick(c, 1);
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    prof_end(c);
+    if (!be.rc && rc == 0 && e == cudaSuccess) kd->n_wit_resident = n_witness;
     if (be.rc) return be.rc;
     if (rc < 0) return rc;
     if (rc > 0) return fail(c, SB_ERR_ARG, err);

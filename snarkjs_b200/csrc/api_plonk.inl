@@ -26,6 +26,7 @@ struct PlonkKeyDev {
     void* work[27] = {nullptr};              // W | 8 x n | 10 x (n + 8) | 8 x 4n   (order of PlonkWork)
     void* d_cub = nullptr; size_t cub_bytes = 0;
     int* d_flag = nullptr; void* d_red = nullptr;
+    std::vector<uint8_t> host_pub; uint64_t n_wit_resident = 0;   // witness[0..nPublic] on the host + length of the witness left in work[0] by the last proof
     void* commit_scratch() const { return work[18]; }   // PlonkWork::scal: free whenever a Montgomery polynomial is committed
 };
 
@@ -39,6 +40,7 @@ void plonk_free_key(PlonkKeyDev* k) {
 // d_ptau, t_ptau, gp, d_pow, pow_h, pow_nhi and commit_scratch()
 template <class F, class K = PlonkKeyDev> struct CudaPlonkBackend {
     sb_ctx* c; K* key; int rc = 0;
+    const void* resident_dst = nullptr;   // set: the witness already sits in this buffer (sb_*_prove_resident), its upload is skipped
     std::chrono::steady_clock::time_point t_mark = std::chrono::steady_clock::now();
     // end of round r: host wall clock since the previous mark (each round ends on a synchronising commit) -> sb_last_ms(r)
     void mark(int r) {
@@ -51,7 +53,7 @@ template <class F, class K = PlonkKeyDev> struct CudaPlonkBackend {
     void launched(const char* what) { c->launches++; note(cudaGetLastError(), what); }
     static unsigned grid(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-    void upload(F* dst, const F* host, size_t n) { note(h2d(c, dst, host, n * sizeof(F)), "plonk upload"); }
+    void upload(F* dst, const F* host, size_t n) { if (dst == resident_dst) return; note(h2d(c, dst, host, n * sizeof(F)), "plonk upload"); }
     void download(F* host, const F* src, size_t n) { note(d2h(c, host, src, n * sizeof(F)), "plonk download"); }
     void zero(F* p, size_t n) { if (n) note(cudaMemsetAsync(p, 0, n * sizeof(F), st()), "plonk memset"); }
     void copy(F* dst, const F* src, size_t n) { if (n) note(cudaMemcpyAsync(dst, src, n * sizeof(F), cudaMemcpyDeviceToDevice, st()), "plonk copy"); }
@@ -262,10 +264,16 @@ template <class PQ, class PR> int plonk_prove_impl(sb_ctx* c, PlonkKeyDev* kd, c
     }
     CudaPlonkBackend<F> be; be.c = c; be.key = kd;
     std::string err;
+    const size_t pub_bytes = ((size_t)z.nPublic + 1) * 32;
+    if (!witness) { witness = kd->host_pub.data(); n_witness = kd->n_wit_resident; be.resident_dst = w.W; }   // resident: only the public signals are read on the host
+    else { kd->n_wit_resident = 0; if (n_witness > z.nPublic) kd->host_pub.assign(witness, witness + pub_bytes); }
     tick(c, 0);
+    prof_begin(c);
     int rc = plonk_prove_flow<PQ, PR>(be, k, w, witness, n_witness, blinders, proof, err);
     tick(c, 1);
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    prof_end(c);
+    if (!be.rc && rc == 0 && e == cudaSuccess) kd->n_wit_resident = n_witness;
     if (be.rc) return be.rc;                                   // a CUDA failure underneath explains whatever the flow reported
     if (rc < 0) return rc;                                     // backend error, message already set
     if (rc > 0) return fail(c, SB_ERR_ARG, err);               // the reference's own Error text

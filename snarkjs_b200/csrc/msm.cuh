@@ -333,6 +333,153 @@ k_window_sum(const XYZZ<F>* __restrict__ partials, uint32_t per_window, XYZZ<F>*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bucket reduction, second design (default): axis sums + warp-shuffle weighted sums.
+//
+// The window sum  sum_b (b+1) * bucket[b]  is  T + sum_b b * bucket[b]  with T = sum of all buckets.  Write the bucket
+// index as b = hi * 2^m + lo (a matrix of H rows by 2^m columns); with the row sums R_hi and the column sums C_lo
+//     sum_b b * bucket[b] = 2^m * sum_hi hi * R_hi + sum_lo lo * C_lo,        T = sum_lo C_lo.
+// Every bucket is added once into a row sum and once into a column sum (2 additions per bucket, the same count as the
+// running-sum recursion of the reference's _reduceTable 5819-5907 or of k_reduce above), but the additions form plain
+// trees: no per-thread scalar multiply and 4x the threads of k_reduce at the first level.
+//   k_axis_sum   out[o][i] = sum_{s<S} in[o][s][i]  (S <= 8 per level; rows and columns of one level in one launch:
+//                the row job views its rows as [S][len/S] so that both jobs read coalesced 128 B .. 4 KiB runs)
+//   k_ws_chunks  one warp per 32 entries of R / C: lane l holds v_l; a shuffle suffix scan gives the suffix sums, their
+//                shuffle-tree sum is sum_l l*v_l (weighted) and the first suffix sum is the plain total
+//   k_ws_final   one CTA per window: the same warp routine over the chunk totals, then the power-of-two weights
+//                (2^m, 2^5) by doublings of single points.
+// ------------------------------------------------------------------------------------------------
+template <class F> __device__ __noinline__ void padd(XYZZ<F>& a, const XYZZ<F>& b) { a.add(b); }
+
+struct AxisJob { const void* in; void* out; uint64_t total; uint32_t S; uint32_t log_inner; };
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_axis_sum(AxisJob j0, AxisJob j1) {
+    const AxisJob j = blockIdx.y ? j1 : j0;
+    const uint64_t gid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (gid >= j.total) return;
+    const uint64_t o = gid >> j.log_inner, i = gid & ((1ull << j.log_inner) - 1);
+    const XYZZ<F>* p = (const XYZZ<F>*)j.in + ((o * j.S) << j.log_inner) + i;
+    XYZZ<F> acc = load_vec(p);
+#pragma unroll 1
+    for (uint32_t s = 1; s < j.S; s++) { XYZZ<F> v = load_vec(p + ((uint64_t)s << j.log_inner)); acc.add(v); }
+    store_vec((XYZZ<F>*)j.out + gid, acc);
+}
+
+template <class F> __device__ __forceinline__ XYZZ<F> shfl_down_pt(const XYZZ<F>& v, int d) {
+    constexpr int NW32 = sizeof(XYZZ<F>) / 4;
+    union U { XYZZ<F> p; uint32_t w[NW32]; __device__ U() {} };
+    U a, r; a.p = v;
+#pragma unroll
+    for (int k = 0; k < NW32; k++) r.w[k] = __shfl_down_sync(0xffffffffu, a.w[k], d);
+    return r.p;
+}
+// lane l holds v_l.  Lane 0 receives T = sum_l v_l and W = sum_l l * v_l (all 32 lanes must call).
+template <class F> __device__ __forceinline__ void warp_weighted_sum(XYZZ<F> v, XYZZ<F>& T, XYZZ<F>& W) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) { XYZZ<F> o = shfl_down_pt<F>(v, d); if (lane + d < 32) padd<F>(v, o); }   // suffix sums
+    T = v;
+    XYZZ<F> x = lane ? v : XYZZ<F>::inf();
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) { XYZZ<F> o = shfl_down_pt<F>(x, d); if (lane < d) padd<F>(x, o); }
+    W = x;
+}
+template <class F> __device__ __forceinline__ XYZZ<F> warp_sum(XYZZ<F> x) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) { XYZZ<F> o = shfl_down_pt<F>(x, d); if (lane < d) padd<F>(x, o); }
+    return x;
+}
+
+// vecR: [NW][lenR] (may be null / lenR = 0), vecC: [NW][lenC].  tw: [NW][nR + nC][2] = (T, W) of every 32-entry chunk.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_ws_chunks(const XYZZ<F>* __restrict__ vecR, uint32_t lenR, const XYZZ<F>* __restrict__ vecC, uint32_t lenC, uint32_t NW, XYZZ<F>* __restrict__ tw) {
+    const uint32_t nR = (lenR + 31) / 32, nC = (lenC + 31) / 32, per = nR + nC;
+    const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid >= NW * per) return;
+    const uint32_t w = wid / per, jj = wid % per;
+    const bool isR = jj < nR;
+    const uint32_t j = isR ? jj : jj - nR, len = isR ? lenR : lenC, idx = j * 32 + lane;
+    const XYZZ<F>* vec = (isR ? vecR : vecC) + (uint64_t)w * len;
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (idx < len) v = load_vec(vec + idx);
+    XYZZ<F> T, W;
+    warp_weighted_sum<F>(v, T, W);
+    if (lane == 0) { store_vec(tw + 2 * (uint64_t)wid, T); store_vec(tw + 2 * (uint64_t)wid + 1, W); }
+}
+
+// window sum = 2^(m+5) * a0 + 2^m * a1 + 2^5 * a2 + a3 + a4 with (chunk index j)
+//   a0 = sum_j j * T^R_j,  a1 = sum_j W^R_j,  a2 = sum_j j * T^C_j,  a3 = sum_j W^C_j,  a4 = sum_j T^C_j (= all buckets).
+template <class F>
+__global__ void __launch_bounds__(128)
+k_ws_final(const XYZZ<F>* __restrict__ tw, uint32_t nR, uint32_t nC, int m, XYZZ<F>* __restrict__ out) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, per = nR + nC;
+    const XYZZ<F>* base = tw + 2 * (uint64_t)blockIdx.x * per;
+    const bool r_side = warp < 2;
+    const uint32_t cnt = r_side ? nR : nC, off = r_side ? 0 : nR;
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (lane < cnt) v = load_vec(base + 2 * (uint64_t)(off + lane) + (warp & 1));   // even warps: T entries, odd warps: W entries
+    int dbl = 0;
+    XYZZ<F> res, tot = XYZZ<F>::inf();
+    if ((warp & 1) == 0) { warp_weighted_sum<F>(v, tot, res); dbl = r_side ? m + 5 : 5; }
+    else { res = warp_sum<F>(v); dbl = r_side ? m : 0; }
+    if (lane == 0) {
+        for (int k = 0; k < dbl; k++) res = XYZZ<F>::dbl(res);
+        store_vec(sm + warp, res);
+        if (warp == 2) store_vec(sm + 4, tot);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ<F> r = load_vec(sm);
+        for (int k = 1; k < 5; k++) { XYZZ<F> t = load_vec(sm + k); padd<F>(r, t); }
+        store_vec(out + blockIdx.x, r);
+    }
+}
+
+// Host plan of the axis-sum levels for one geometry.  Buckets of a window form H = 2^er rows... of 2^m columns
+// (m = WS_COL_BITS when the window has more than 2^m buckets, else there is no split and C = the buckets themselves).
+static constexpr int WS_COL_BITS = 10;
+struct WsPlan {
+    bool ok = false;                 // false: geometry outside the design (more than 2^20 buckets per window) -> k_reduce
+    int m = 0, er = 0, ec = 0;       // column bits, bits the row chain reduces (= m), bits the column chain reduces
+    int levels = 0; int br[8] = {0}, bc[8] = {0};
+    uint32_t lenR = 0, lenC = 0, nR = 0, nC = 0;
+    size_t rowA = 0, rowB = 0, colA = 0, colB = 0, tw = 0;   // scratch sizes in XYZZ elements
+    size_t elems() const { return rowA + rowB + colA + colB + tw + 8; }
+};
+__host__ inline WsPlan ws_plan(const MsmGeom& g) {
+    WsPlan p; const int cbits = g.c - 1; const size_t NW = g.windows();
+    if (cbits > 2 * WS_COL_BITS || cbits < 0) return p;
+    p.ok = true;
+    if (cbits > WS_COL_BITS) { p.m = WS_COL_BITS; p.er = p.m; p.ec = cbits - p.m; p.lenR = 1u << p.ec; p.lenC = 1u << p.m; }
+    else { p.lenR = 0; p.lenC = g.B; }
+    int rr = p.er, rc = p.ec;
+    while (rr > 0 || rc > 0) {
+        const int l = p.levels++;
+        p.br[l] = rr < 3 ? rr : 3; p.bc[l] = rc < 3 ? rc : 3; rr -= p.br[l]; rc -= p.bc[l];
+        const size_t orow = p.br[l] ? (NW * g.B) >> (p.er - rr) : 0, ocol = p.bc[l] ? (NW * g.B) >> (p.ec - rc) : 0;
+        if (l & 1) { if (orow > p.rowB) p.rowB = orow; if (ocol > p.colB) p.colB = ocol; }
+        else { if (orow > p.rowA) p.rowA = orow; if (ocol > p.colA) p.colA = ocol; }
+    }
+    p.nR = (p.lenR + 31) / 32; p.nC = (p.lenC + 31) / 32;
+    p.tw = 2 * NW * (p.nR + p.nC);
+    return p;
+}
+// scratch (in XYZZ elements) of the reduction: k_reduce partials, or the axis-sum ping-pong buffers + chunk pairs
+__host__ inline size_t msm_reduce_scratch_elems(const MsmGeom& g) {
+    const uint32_t NW = g.windows();
+    const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
+    const uint32_t ctas_per_window = (g.B / L + 127) / 128;
+    const size_t legacy = (size_t)2 * NW * ctas_per_window;
+    const WsPlan p = ws_plan(g);
+    return (p.ok && p.elems() > legacy) ? p.elems() : legacy;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Precomputed window multiples for a registered base set: table[w*n + i] = 2^(c*w) * P_i (affine), w < W.
 // One thread per point: c doublings per window in XYZZ, one inversion per table entry.  One-time cost per key.
 // ------------------------------------------------------------------------------------------------
@@ -409,14 +556,14 @@ extern int g_msm_tuning[8];
 struct MsmLaunchStats {
     int launches = 0;
     // optional profiling: event pairs recorded around kernel groups (tag = PROF_* below; accumulation uses cur_tag)
-    cudaEvent_t* ev = nullptr; int nev = 0; int used = 0; int tag[32] = {0}; int cur_tag = 0;
+    cudaEvent_t* ev = nullptr; int nev = 0; int used = 0; int tag[128] = {0}; int cur_tag = 0;
 };
 enum { PROF_ACC_G1 = 1, PROF_ACC_G2 = 2, PROF_SORT = 3, PROF_FOLD = 4, PROF_REDUCE = 5, PROF_QAP = 6, PROF_NTT = 7, PROF_JOIN = 8 };
 // one event pair around a group of launches on `st`; a no-op unless profiling is armed (api.cu prof_begin)
 struct ProfScope {
     MsmLaunchStats* s; cudaStream_t st; int idx = -1;
     ProfScope(MsmLaunchStats* s_, int tag, cudaStream_t st_) : s(s_), st(st_) {
-        if (s && s->ev && s->used + 2 <= s->nev && s->used / 2 < 32) { idx = s->used; s->used += 2; s->tag[idx / 2] = tag; cudaEventRecord(s->ev[idx], st); }
+        if (s && s->ev && s->used + 2 <= s->nev && s->used / 2 < 128) { idx = s->used; s->used += 2; s->tag[idx / 2] = tag; cudaEventRecord(s->ev[idx], st); }
     }
     void end() { if (idx >= 0) { cudaEventRecord(s->ev[idx + 1], st); idx = -1; } }
     void end(cudaStream_t other) { st = other; end(); }
@@ -480,7 +627,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
         const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
         const uint32_t ctas_per_window = (g.B / L + 127) / 128;
         size_t need = al(NBl * sizeof(XYZZ<F>)) + al(heads0 * sizeof(XYZZ<F>)) + al(heads0 * 4) + al(heads1 * sizeof(XYZZ<F>)) + al(heads1 * 4) +
-                      al(heads0 * 4) + al((size_t)2 * g.windows() * ctas_per_window * sizeof(XYZZ<F>));
+                      al(heads0 * 4) + al(msm_reduce_scratch_elems(g) * sizeof(XYZZ<F>));
         need += need / 8 + (1u << 20);   // margin: the impl must never grow (= reallocate) the scratch the rounds are using
         if (!scratch.get(o_rest + need)) return (int)cudaErrorMemoryAllocation;
     }
@@ -537,7 +684,7 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
     size_t o_headsB = o_hkA + al(heads0 * 4), o_hkB = o_headsB + al(heads1 * sizeof(XYZZ<F>));
     size_t o_hkM = o_hkB + al(heads1 * 4);                     // level-1 keys after the short-run fast path
     size_t o_part = o_hkM + al(heads0 * 4);
-    size_t bytes = o_part + al((size_t)2 * NW * ctas_per_window * sizeof(XYZZ<F>));   // x2: (R, S) pairs of k_reduce2
+    size_t bytes = o_part + al(msm_reduce_scratch_elems(g) * sizeof(XYZZ<F>));
     uint8_t* base = (uint8_t*)scratch.get(scratch_off + bytes);
     if (!base) return (int)cudaErrorMemoryAllocation;
     base += scratch_off;
@@ -589,7 +736,25 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
     }
     if (!heads0 && tail_stream && tail_stream != stream && ev_acc) { cudaEventRecord(ev_acc, stream); cudaStreamWaitEvent(tail_stream, ev_acc, 0); stream = tail_stream; }
     ProfScope pred(stats, PROF_REDUCE, stream);
-    if (g.B >= (uint32_t)RED2_BUCKETS && g.B / RED2_BUCKETS <= 1024 && g_msm_tuning[1] == 2) {   // experimental: less work (-36 %) but 2-3x the
+    const WsPlan wp = ws_plan(g);
+    if (wp.ok && g_msm_tuning[1] == 0) {
+        // axis sums (rows and columns of one level per launch), then the warp-shuffle weighted sums
+        XYZZ<F>* rowb[2] = {partials, partials + wp.rowA};
+        XYZZ<F>* colb[2] = {partials + wp.rowA + wp.rowB, partials + wp.rowA + wp.rowB + wp.colA};
+        XYZZ<F>* tw = partials + wp.rowA + wp.rowB + wp.colA + wp.colB;
+        const XYZZ<F>* rin = buckets; const XYZZ<F>* cin = buckets;
+        int rr = wp.er, rc = wp.ec;
+        for (int l = 0; l < wp.levels; l++) {
+            AxisJob jr{nullptr, nullptr, 0, 1, 0}, jc{nullptr, nullptr, 0, 1, 0};
+            if (wp.br[l]) { rr -= wp.br[l]; jr = AxisJob{rin, rowb[l & 1], (uint64_t)nbuckets >> (wp.er - rr), 1u << wp.br[l], (uint32_t)rr}; rin = rowb[l & 1]; }
+            if (wp.bc[l]) { rc -= wp.bc[l]; jc = AxisJob{cin, colb[l & 1], (uint64_t)nbuckets >> (wp.ec - rc), 1u << wp.bc[l], (uint32_t)wp.m}; cin = colb[l & 1]; }
+            const uint64_t mx = jr.total > jc.total ? jr.total : jc.total;
+            k_axis_sum<F><<<dim3((unsigned)((mx + 127) / 128), 2), 128, 0, stream>>>(jr, jc); launches++;
+        }
+        const uint32_t per = wp.nR + wp.nC;
+        k_ws_chunks<F><<<(NW * per + 3) / 4, 128, 0, stream>>>(wp.lenR ? rin : nullptr, wp.lenR, cin, wp.lenC, NW, tw); launches++;
+        k_ws_final<F><<<NW, 128, 5 * sizeof(XYZZ<F>), stream>>>(tw, wp.nR, wp.nC, wp.m, d_wsum); launches++;
+    } else if (g.B >= (uint32_t)RED2_BUCKETS && g.B / RED2_BUCKETS <= 1024 && g_msm_tuning[1] == 2) {   // experimental: less work (-36 %) but 2-3x the
         // dependent-add latency of k_reduce; measured slower (proof 27.4 ms vs 26.0 ms overlapped, 31.3 vs 26.6 serialised)
         // hierarchical reduction: per-CTA (R, S) pairs live in the partials area (2 * NC entries per window <= ctas_per_window)
         const uint32_t NC = g.B / RED2_BUCKETS;

@@ -1,6 +1,7 @@
 // Host backend shared by host_plonk.cpp and host_fflonk.cpp: the Backend concept of plonk_flow.h implemented with plain
 // loops over the plonk.cuh element functions; NTT / MSM are borrowed from the CPU oracle (function pointers filled by
-// the caller from dlopen).  Test infrastructure only.
+// the caller from dlopen).  Test infrastructure only.  The independent element loops carry OpenMP pragmas: bench.py's
+// reference arm compiles this with -fopenmp as the multi-threaded CPU port of plonk prove / fflonk prove.
 #pragma once
 #include <cstdio>
 #include <cstring>
@@ -38,7 +39,7 @@ template <class F> struct HostBackend {
     }
     int commit(const F* coef, uint64_t len, uint8_t* affine) {
         std::vector<F> s(len);
-        for (uint64_t i = 0; i < len; i++) s[i] = F::from_mont(coef[i]);
+        _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < len; i++) s[i] = F::from_mont(coef[i]);
         return commit_plain(s.data(), len, affine);
     }
     void additions(const PlonkKeyView<F>& k, F* W) {
@@ -47,13 +48,13 @@ template <class F> struct HostBackend {
     }
     void wires(const PlonkKeyView<F>& k, const F* W, F* A, F* B, F* C) {
         F* out[3] = {A, B, C};
-        for (int j = 0; j < 3; j++) for (uint64_t i = 0; i < k.n; i++) pl_wire<F>(i, k.map[j], W, k.nVars, k.nConstraints, out[j]);
+        for (int j = 0; j < 3; j++) { _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < k.n; i++) pl_wire<F>(i, k.map[j], W, k.nVars, k.nConstraints, out[j]); }
     }
     void blind(F* p, uint64_t n, const F* bf, int cnt) { pl_blind<F>(p, n, bf, cnt); }
     int z(const PlonkKeyView<F>& k, const PlonkRound<F>& r, PlonkWork<F>& w) {
         const uint64_t n = k.n;
-        for (uint64_t i = 0; i < n; i++) pl_z_terms<F>(i, w.bufA, w.bufB, w.bufC, k.s_ev[0], k.s_ev[1], k.s_ev[2], k.wpow, r, w.num, w.den);
-        for (uint64_t lo = 0; lo < n; lo += 16) pl_ratio_chunk<F>(w.den, w.num, w.ratio, lo, lo + 16 < n ? lo + 16 : n);
+        _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < n; i++) pl_z_terms<F>(i, w.bufA, w.bufB, w.bufC, k.s_ev[0], k.s_ev[1], k.s_ev[2], k.wpow, r, w.num, w.den);
+        _Pragma("omp parallel for schedule(static)") for (uint64_t lo = 0; lo < n; lo += 16) pl_ratio_chunk<F>(w.den, w.num, w.ratio, lo, lo + 16 < n ? lo + 16 : n);
         F acc = F::one();
         for (uint64_t i = 0; i < n; i++) { w.bufZ[i] = acc; acc = F::mul(acc, w.ratio[i]); }     // exclusive product scan
         return (F::mul(w.bufZ[n - 1], w.ratio[n - 1]) == F::one()) ? 0 : 4;
@@ -63,10 +64,10 @@ template <class F> struct HostBackend {
         in.A = w.evA; in.B = w.evB; in.C = w.evC; in.Z = w.evZ;
         in.QM = k.q_ev[0]; in.QL = k.q_ev[1]; in.QR = k.q_ev[2]; in.QO = k.q_ev[3]; in.QC = k.q_ev[4];
         in.S1 = k.s_ev[0]; in.S2 = k.s_ev[1]; in.S3 = k.s_ev[2]; in.LAG = k.lag; in.pubA = w.bufA; in.n_public = k.nPublic;
-        for (uint64_t i = 0; i < 4ull * k.n; i++) pl_t_eval<F>(i, 4ull * k.n, in, k.w4pow, r, w.T, w.Tz);
+        _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < 4ull * k.n; i++) pl_t_eval<F>(i, 4ull * k.n, in, k.w4pow, r, w.T, w.Tz);
     }
-    int divzh(uint64_t n, const F* t, const F* tz, F* out) { int f = 0; for (uint64_t i = 0; i < n; i++) f |= pl_divzh<F>(i, n, t, tz, out); return f; }
-    void tsplit(uint64_t n, const F* t, const F& b10, const F& b11, F* T1, F* T2, F* T3) { for (uint64_t i = 0; i < n + 6; i++) pl_tsplit<F>(i, n, t, b10, b11, T1, T2, T3); }
+    int divzh(uint64_t n, const F* t, const F* tz, F* out) { int f = 0; _Pragma("omp parallel for schedule(static) reduction(|:f)") for (uint64_t i = 0; i < n; i++) f |= pl_divzh<F>(i, n, t, tz, out); return f; }
+    void tsplit(uint64_t n, const F* t, const F& b10, const F& b11, F* T1, F* T2, F* T3) { _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < n + 6; i++) pl_tsplit<F>(i, n, t, b10, b11, T1, T2, T3); }
     void make_pow(const F& base, uint64_t count, PlonkPow<F>& out, int) {
         int h = plonk_pow_h(count);
         std::vector<F> lo, hi; plonk_pow_tables<F>(base, h, (count >> h) + 1, lo, hi);
@@ -74,13 +75,20 @@ template <class F> struct HostBackend {
         pow_store.push_back(hi); out.hi = pow_store.back().data(); out.h = h;
     }
     F eval(const F* f, uint64_t len, const PlonkPow<F>& pw, F*, F*) {
+        // field addition is exact: any grouping of the sum gives the same element, so the chunks may run in parallel
+        const uint64_t CH = 64; std::vector<F> part(CH, F::zero());
+        _Pragma("omp parallel for schedule(static)") for (uint64_t c = 0; c < CH; c++) {
+            F s = F::zero(); const uint64_t lo = len * c / CH, hi = len * (c + 1) / CH;
+            for (uint64_t i = lo; i < hi; i++) s = F::add(s, F::mul(f[i], pl_pow(pw, i)));
+            part[c] = s;
+        }
         F s = F::zero();
-        for (uint64_t i = 0; i < len; i++) s = F::add(s, F::mul(f[i], pl_pow(pw, i)));
+        for (uint64_t c = 0; c < CH; c++) s = F::add(s, part[c]);
         return s;
     }
     int quotient(const F* f, const PlonkLinIn* lin, const PlonkLin<F>* L, uint64_t n, uint64_t len, uint64_t m, const F& sub0,
                  const PlonkPow<F>& pw, const PlonkPow<F>& ipw, F* g, F* P, F* q_plain) {
-        for (uint64_t i = 0; i < m; i++) {
+        _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < m; i++) {
             F x;
             if (lin) x = pl_wxi_coef<F>(i, n, *lin, *L);
             else { x = i < len ? f[i] : F::zero(); if (i == 0) x = F::sub(x, sub0); }
@@ -88,7 +96,7 @@ template <class F> struct HostBackend {
         }
         F acc = F::zero();
         for (uint64_t i = 0; i < m; i++) { acc = F::add(acc, g[i]); P[i] = acc; }                    // inclusive sum scan
-        for (uint64_t j = 0; j < m; j++) q_plain[j] = F::from_mont(pl_quot_coef<F>(j, m, P, ipw));
+        _Pragma("omp parallel for schedule(static)") for (uint64_t j = 0; j < m; j++) q_plain[j] = F::from_mont(pl_quot_coef<F>(j, m, P, ipw));
         return P[m - 1].is_zero() ? 0 : 1;
     }
 };

@@ -6,27 +6,27 @@
 
 template <class F> struct HostFflonkBackend : HostBackend<F> {
     void wire_blind(F* A, F* B, F* C, uint64_t n, const F raw[6]) { F* bufs[3] = {A, B, C}; for (int j = 0; j < 3; j++) ff_wire_blind<F>(bufs[j], n, raw[2 * j], raw[2 * j + 1]); }
-    void t0(const PlonkTIn& in, uint64_t n4, F* T0) { for (uint64_t i = 0; i < n4; i++) ff_t0<F>(i, n4, in, T0); }
-    void t1(uint64_t n2, const F* evZ, const F* lag1, const PlonkPow<F>& w2pow, const PlonkRound<F>& r, F* T1, F* T1z) { for (uint64_t i = 0; i < n2; i++) ff_t1<F>(i, evZ, lag1, w2pow, r, T1, T1z); }
-    void t2(const PlonkTIn& in, uint64_t n4, const PlonkPow<F>& w4pow, const PlonkRound<F>& r, F* T2, F* T2z) { for (uint64_t i = 0; i < n4; i++) ff_t2<F>(i, n4, in, w4pow, r, T2, T2z); }
-    int divzh_n(uint64_t n, int blocks, const F* t, const F* tz, F* out, uint64_t bound) { int f = 0; for (uint64_t i = 0; i < n; i++) f |= ff_divzh<F>(i, n, blocks, t, tz, out, bound); return f; }
-    void interleave(const FfParts& parts, uint64_t total, F* out) { for (uint64_t k = 0; k < total; k++) ff_interleave<F>(k, parts, out); }
+    void t0(const PlonkTIn& in, uint64_t n4, F* T0) { _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < n4; i++) ff_t0<F>(i, n4, in, T0); }
+    void t1(uint64_t n2, const F* evZ, const F* lag1, const PlonkPow<F>& w2pow, const PlonkRound<F>& r, F* T1, F* T1z) { _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < n2; i++) ff_t1<F>(i, evZ, lag1, w2pow, r, T1, T1z); }
+    void t2(const PlonkTIn& in, uint64_t n4, const PlonkPow<F>& w4pow, const PlonkRound<F>& r, F* T2, F* T2z) { _Pragma("omp parallel for schedule(static)") for (uint64_t i = 0; i < n4; i++) ff_t2<F>(i, n4, in, w4pow, r, T2, T2z); }
+    int divzh_n(uint64_t n, int blocks, const F* t, const F* tz, F* out, uint64_t bound) { int f = 0; _Pragma("omp parallel for schedule(static) reduction(|:f)") for (uint64_t i = 0; i < n; i++) f |= ff_divzh<F>(i, n, blocks, t, tz, out, bound); return f; }
+    void interleave(const FfParts& parts, uint64_t total, F* out) { _Pragma("omp parallel for schedule(static)") for (uint64_t k = 0; k < total; k++) ff_interleave<F>(k, parts, out); }
     int quot_m(const F* f, uint64_t len, const FfSmall<F>& R, const F& scale, int m, uint64_t rows, const PlonkPow<F>& bpow, const PlonkPow<F>& ibpow, F* G, F* P, F* q) {
         const uint64_t total = rows * m;
         std::vector<F> src(f, f + (len < total ? len : total));           // f may alias q (second division of f3)
-        for (uint64_t k = 0; k < total; k++) ff_qm_g<F>(k, src.data(), src.size(), R, scale, m, rows, bpow, G);
+        _Pragma("omp parallel for schedule(static)") for (uint64_t k = 0; k < total; k++) ff_qm_g<F>(k, src.data(), src.size(), R, scale, m, rows, bpow, G);
         for (int j = 0; j < m; j++) { F acc = F::zero(); for (uint64_t t = 0; t < rows; t++) { acc = F::add(acc, G[j * rows + t]); P[j * rows + t] = acc; } }   // segmented scan
         int bad = 0;
-        for (uint64_t k = 0; k < total; k++) bad |= ff_qm_q<F>(k, m, rows, P, ibpow, q);
+        _Pragma("omp parallel for schedule(static) reduction(|:bad)") for (uint64_t k = 0; k < total; k++) bad |= ff_qm_q<F>(k, m, rows, P, ibpow, q);
         return bad;
     }
-    void add3(uint64_t total, const F* a, const F* b, const F* c, F* out) { for (uint64_t k = 0; k < total; k++) out[k] = F::add(F::add(a[k], b[k]), c[k]); }
+    void add3(uint64_t total, const F* a, const F* b, const F* c, F* out) { _Pragma("omp parallel for schedule(static)") for (uint64_t k = 0; k < total; k++) out[k] = F::add(F::add(a[k], b[k]), c[k]); }
     int quot_l(uint64_t total, const F* C0, uint64_t l0, const F* C1, uint64_t l1, const F* C2, uint64_t l2, const F* Fp, uint64_t lf,
                const FfLin<F>& L, const PlonkPow<F>& ypow, const PlonkPow<F>& iypow, F* g, F* P, F* q_plain) {
-        for (uint64_t k = 0; k < total; k++) g[k] = F::mul(ff_l_coef<F>(k, C0, l0, C1, l1, C2, l2, Fp, lf, L), pl_pow(ypow, k));
+        _Pragma("omp parallel for schedule(static)") for (uint64_t k = 0; k < total; k++) g[k] = F::mul(ff_l_coef<F>(k, C0, l0, C1, l1, C2, l2, Fp, lf, L), pl_pow(ypow, k));
         F acc = F::zero();
         for (uint64_t k = 0; k < total; k++) { acc = F::add(acc, g[k]); P[k] = acc; }
-        for (uint64_t j = 0; j < total; j++) q_plain[j] = F::from_mont(pl_quot_coef<F>(j, total, P, iypow));
+        _Pragma("omp parallel for schedule(static)") for (uint64_t j = 0; j < total; j++) q_plain[j] = F::from_mont(pl_quot_coef<F>(j, total, P, iypow));
         return P[total - 1].is_zero() ? 0 : 1;
     }
 };

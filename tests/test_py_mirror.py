@@ -69,3 +69,35 @@ def test_fflonk_mirror_header_and_proof_object(tmp_path_factory, golden):
     assert got == want and list(got["evaluations"]) == list(want["evaluations"])
     with pytest.raises(SbError, match="zkey file is not fflonk"):
         sb_fflonk.read_zkey_header_fflonk(bytes(golden("plonk_case.npz")["zkey"]))
+
+
+def _oracle_callbacks(ci):
+    """The builders' field callables backed by the CPU oracle (what bench.py's reference arm uses)."""
+    wn_of = lambda p: ci.fr_from_mont(orc.fr_root(ci.id, p))
+    return (wn_of, lambda b, inv: orc.fr_fft(ci.id, b, inv), lambda b, f, i: orc.fr_batch_apply_key(ci.id, b, f, i),
+            lambda grp, sd, k: orc.gen_points(ci.id, grp, sd, k), ci.g2_affine_bytes(ci.g2))
+
+
+@pytest.mark.parametrize("curve_id,n_gates", [(orc.BN254, 26), (orc.BN254, 500), (orc.BLS12_381, 120)])
+def test_synth_plonk_key_builder_equals_oracle_setup(curve_id, n_gates):
+    """snarkjs_b200/synth.py builds the bench's PLONK keys with numpy + the library's NTT; with the oracle's NTT behind the
+    same callables it must give the bytes of oracle.plonk.plonk_setup_synth (the restated plonk_setup.js) for the same gates."""
+    from snarkjs_b200 import synth
+    ci = orc.CURVES[curve_id]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(n_gates, r=ci.r)
+    want = op.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=4242, structured=False, curve=curve_id)
+    circ = synth.plonk_chain_circuit(n_gates, ci.r)
+    assert circ["n_vars"] == n_vars and circ["witness"].tobytes() == b"".join(int(x).to_bytes(32, "little") for x in wit)
+    got = synth.plonk_zkey_image(ci.q, ci.r, ci.n8q, circ, *_oracle_callbacks(ci), seed=4242)
+    assert got == want
+
+
+@pytest.mark.parametrize("n_gates", [26, 300])
+def test_synth_fflonk_key_builder_equals_oracle_setup(n_gates):
+    from snarkjs_b200 import synth
+    ci = orc.CURVES[orc.BN254]
+    gates, adds, n_vars, n_pub, wit = op.chain_gates(n_gates)
+    want = off.fflonk_setup_synth(gates, adds, n_vars, n_pub, tau=4242, structured=False)
+    circ = synth.plonk_chain_circuit(n_gates, ci.r)
+    got = synth.fflonk_zkey_image(ci.q, ci.r, ci.n8q, circ, *_oracle_callbacks(ci), seed=4242)
+    assert got == want
