@@ -304,8 +304,7 @@ def run_b200(args):
 
     if rank != 0:
         return
-    # dominant kernel: the bucket-accumulation kernel (G1: 10 Fq modmul per entry, XYZZ mixed add 8M+2S;
-    # G2: 8 Fq2 mul + 2 Fq2 sqr = 28 Fq modmul per entry).  Algorithmic bytes per entry: 8 B sorted (key,val) +
+    # dominant kernel: the bucket-accumulation kernel (XYZZ mixed add 8M+2S per entry; G2: 8 Fq2 mul + 2 Fq2 sqr).  Algorithmic bytes per entry: 8 B sorted (key,val) +
     # one affine base (64 / 128 B), plus the bucket array written once.
     peaks = {}
     try:
@@ -314,8 +313,11 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    g1_mod = acc["g1_entries"] * 10.0
-    g2_mod = acc["g2_entries"] * 28.0
+    # multiply-equivalents per entry from the wide-MAC count (one 8-limb Montgomery multiply = 2*64 + 8 = 136 wide MACs, a
+    # dual-product multiply = 3*64 + 8 = 200): G1 mixed add = 8 multiplies + 1 dual = 1288 MACs = 9.47; G2 = 16 duals + 4
+    # multiplies = 3744 MACs = 27.53
+    g1_mod = acc["g1_entries"] * (1288.0 / 136.0)
+    g2_mod = acc["g2_entries"] * (3744.0 / 136.0)
     dom = "g2" if acc["g2_ms"] >= acc["g1_ms"] / max(acc["g1_launches"], 1) else "g1"
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)

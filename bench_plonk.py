@@ -235,11 +235,13 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n32 = curve.n8q // 4
-    # dominant kernel: G1 bucket accumulation over the PTau window table (10 Fq modmul per entry, 8 B entry + one affine base)
+    # dominant kernel: G1 bucket accumulation over the PTau window table (8 B entry + one affine base per entry)
     alg_bytes = acc_entries * (8 + 2 * curve.n8q) / acc_launches
     avg_ms = acc_ms / acc_launches
     ach_gbs = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    ach_mod = (acc_entries * 10.0 / acc_launches) / (avg_ms * 1e-3) if avg_ms > 0 else 0.0
+    # 8 multiplies + 1 dual-product multiply per mixed add, in multiply-equivalents by wide-MAC count (N = limbs)
+    mod_per_entry = (8 * (2 * n32 * n32 + n32) + (3 * n32 * n32 + n32)) / (2 * n32 * n32 + n32)   # 3p < 2^(32 N) for both base fields: the dual product applies
+    ach_mod = (acc_entries * mod_per_entry / acc_launches) / (avg_ms * 1e-3) if avg_ms > 0 else 0.0
     # integer-pipe peak for this base field: the calibrated BN254 rate scaled by the wide-MAC count of one multiply (2N^2 + N)
     peak_mod = peak_modmul_bn * (2 * 8 * 8 + 8) / (2 * n32 * n32 + n32)
     traffic = None

@@ -389,12 +389,12 @@ int msm_dev_accumulate(sb_ctx* c, const GroupOps& G, const void* d_bases, const 
         MsmSorted s;
         int rc = msm_sort_entries(d_scalars + off * sbytes, sbytes, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
-        void* d_wsum = c->io[3].get((size_t)g.windows() * G.xyzz_bytes);
+        void* d_wsum = c->io[3].get((size_t)g.wsum_points() * G.xyzz_bytes);
         if (!d_wsum) return fail(c, SB_ERR_NOMEM, "out of device memory");
         c->stats.cur_tag = (&G == &c->g1) ? SB_G1 : SB_G2;
         rc = G.buckets(gp ? d_bases : (const void*)((const uint8_t*)d_bases + off * G.aff_bytes), s, c->bucket_scratch, c->stream, d_wsum, &c->stats, nullptr, nullptr);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_buckets");
-        std::vector<uint8_t> ws((size_t)g.windows() * G.xyzz_bytes);
+        std::vector<uint8_t> ws((size_t)g.wsum_points() * G.xyzz_bytes);
         uint64_t entries = 0;
         CU(c, cudaMemcpyAsync(ws.data(), d_wsum, ws.size(), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(&entries, s.counts, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -716,7 +716,8 @@ int sb_fr_root(sb_ctx* c, int what, uint8_t out[32]) { SB_LOCK(c);
 int sb_set_tuning(int key, int value) {
     if (key == 8) { g_stage_enabled = value; return 0; }                                                      // pinned staging of pageable buffers
     if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
-    if (key < 0 || key >= 8) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
+    if (key == 9) { g_msm_tuning[7] = value; return 0; }                                                      // forced entries per accumulation thread (0 = adaptive)
+    if (key < 0 || key >= 7) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
 }
 double sb_last_stat(sb_ctx* c, int which) { SB_LOCK(c); return (c && which >= 0 && which < 16) ? c->stat[which] : 0.0; }
 double sb_calibrate(sb_ctx* c, int what) { SB_LOCK(c); if (!c) return -1; cudaSetDevice(c->device); return calibrate(what, c->stream); }
@@ -1154,7 +1155,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         MsmGeom gw = msm_geometry(wcnt, 32, c->fr_bits), gh = msm_geometry(hcnt, 32, c->fr_bits);
         const bool pre = k->tA != nullptr;
         if (pre) { gw = k->gpW; gw.first = wb; gh = k->gpH; gh.first = hb; }
-        const size_t w1 = (size_t)gw.windows() * G1.xyzz_bytes, w2 = (size_t)gw.windows() * G2.xyzz_bytes, wh = (size_t)gh.windows() * G1.xyzz_bytes;
+        const size_t w1 = (size_t)gw.wsum_points() * G1.xyzz_bytes, w2 = (size_t)gw.wsum_points() * G2.xyzz_bytes, wh = (size_t)gh.wsum_points() * G1.xyzz_bytes;
         if (3 * w1 + w2 + wh + 64 > 256 * 1024 || 3 * w1 + w2 + wh > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
         uint8_t* dws = (uint8_t*)k->dWsum; uint8_t* hws = c->pinned;
         uint64_t* hcounts = (uint64_t*)(c->pinned + 3 * w1 + w2 + wh);
@@ -1212,7 +1213,7 @@ static int groth16_device(sb_ctx* c, Groth16Key* k, const uint8_t* witness, uint
         rc = msm_sort_entries((const uint8_t*)k->dW + (wlo + off) * 32, 32, cn, g, c->sort_scratch, c->stream, &s, &c->stats);
         if (rc) return cuda_fail(c, (cudaError_t)rc, "msm_sort_entries");
         uint8_t* ws = (uint8_t*)k->dWsum;
-        size_t w1 = (size_t)g.W * G1.xyzz_bytes, w2 = (size_t)g.W * G2.xyzz_bytes;
+        size_t w1 = (size_t)g.wsum_points() * G1.xyzz_bytes, w2 = (size_t)g.wsum_points() * G2.xyzz_bytes;
         if (3 * w1 + w2 > (size_t)8 * 80 * 4 * 96) return fail(c, SB_ERR_ARG, "window buffer too small");
         c->stats.cur_tag = SB_G1;
         rc = G1.buckets((const uint8_t*)k->dA + base * G1.aff_bytes, s, c->bucket_scratch, c->stream, ws, &c->stats, nullptr, nullptr); if (rc) return cuda_fail(c, (cudaError_t)rc, "msm A");

@@ -108,12 +108,12 @@ template <class F, int MINB>
 __global__ void __launch_bounds__(MSM_ACC_THREADS, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const uint64_t* __restrict__ counts, XYZZ<F>* __restrict__ buckets,
-             XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
+             XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys, uint32_t seg) {
     const uint64_t M = counts[0];
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint64_t lo = t * MSM_SEG;
+    uint64_t lo = t * seg;
     if (lo >= M) return;
-    uint64_t hi = lo + MSM_SEG < M ? lo + MSM_SEG : M;
+    uint64_t hi = lo + seg < M ? lo + seg : M;
     const F one = F::one();
     XYZZ<F> acc = XYZZ<F>::inf();
     uint32_t cur = keys[lo];
@@ -378,17 +378,17 @@ template <class F> __device__ __forceinline__ XYZZ<F> shfl_down_pt(const XYZZ<F>
 template <class F> __device__ __forceinline__ void warp_weighted_sum(XYZZ<F> v, XYZZ<F>& T, XYZZ<F>& W) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) { XYZZ<F> o = shfl_down_pt<F>(v, d); if (lane + d < 32) padd<F>(v, o); }   // suffix sums
+    for (int d = 1; d < 32; d <<= 1) { XYZZ<F> o = shfl_down_pt<F>(v, d); if (lane + d < 32) v.add(o); }   // suffix sums
     T = v;
     XYZZ<F> x = lane ? v : XYZZ<F>::inf();
 #pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) { XYZZ<F> o = shfl_down_pt<F>(x, d); if (lane < d) padd<F>(x, o); }
+    for (int d = 16; d >= 1; d >>= 1) { XYZZ<F> o = shfl_down_pt<F>(x, d); if (lane < d) x.add(o); }
     W = x;
 }
 template <class F> __device__ __forceinline__ XYZZ<F> warp_sum(XYZZ<F> x) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) { XYZZ<F> o = shfl_down_pt<F>(x, d); if (lane < d) padd<F>(x, o); }
+    for (int d = 16; d >= 1; d >>= 1) { XYZZ<F> o = shfl_down_pt<F>(x, d); if (lane < d) x.add(o); }
     return x;
 }
 
@@ -412,32 +412,45 @@ k_ws_chunks(const XYZZ<F>* __restrict__ vecR, uint32_t lenR, const XYZZ<F>* __re
 
 // window sum = 2^(m+5) * a0 + 2^m * a1 + 2^5 * a2 + a3 + a4 with (chunk index j)
 //   a0 = sum_j j * T^R_j,  a1 = sum_j W^R_j,  a2 = sum_j j * T^C_j,  a3 = sum_j W^C_j,  a4 = sum_j T^C_j (= all buckets).
+// One CTA of four warps per window writes the five parts out[5 w + k]; the power-of-two weights (m + 10 doublings of single
+// points: pure latency here) are applied by the host (msm_group.inl combine).
 template <class F>
 __global__ void __launch_bounds__(128)
-k_ws_final(const XYZZ<F>* __restrict__ tw, uint32_t nR, uint32_t nC, int m, XYZZ<F>* __restrict__ out) {
-    extern __shared__ uint4 smem_raw[];
-    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+k_ws_final(const XYZZ<F>* __restrict__ tw, uint32_t nR, uint32_t nC, XYZZ<F>* __restrict__ out) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, per = nR + nC;
     const XYZZ<F>* base = tw + 2 * (uint64_t)blockIdx.x * per;
     const bool r_side = warp < 2;
     const uint32_t cnt = r_side ? nR : nC, off = r_side ? 0 : nR;
     XYZZ<F> v = XYZZ<F>::inf();
     if (lane < cnt) v = load_vec(base + 2 * (uint64_t)(off + lane) + (warp & 1));   // even warps: T entries, odd warps: W entries
-    int dbl = 0;
-    XYZZ<F> res, tot = XYZZ<F>::inf();
-    if ((warp & 1) == 0) { warp_weighted_sum<F>(v, tot, res); dbl = r_side ? m + 5 : 5; }
-    else { res = warp_sum<F>(v); dbl = r_side ? m : 0; }
-    if (lane == 0) {
-        for (int k = 0; k < dbl; k++) res = XYZZ<F>::dbl(res);
-        store_vec(sm + warp, res);
-        if (warp == 2) store_vec(sm + 4, tot);
+    XYZZ<F>* o = out + 5 * (uint64_t)blockIdx.x;
+    if ((warp & 1) == 0) {
+        XYZZ<F> tot, res;
+        warp_weighted_sum<F>(v, tot, res);
+        if (lane == 0) { store_vec(o + (r_side ? 0 : 2), res); if (!r_side) store_vec(o + 4, tot); }
+    } else {
+        XYZZ<F> res = warp_sum<F>(v);
+        if (lane == 0) store_vec(o + (r_side ? 1 : 3), res);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        XYZZ<F> r = load_vec(sm);
-        for (int k = 1; k < 5; k++) { XYZZ<F> t = load_vec(sm + k); padd<F>(r, t); }
-        store_vec(out + blockIdx.x, r);
-    }
+}
+
+// One warp per output: out[o][i] = sum_{s<S} in[o][s][i], S <= 128: lane l adds s = l, l + 32, ... and a shuffle tree joins
+// the lanes.  Used for everything the first axis-sum level leaves (2^16 partials per chain at 2^19 buckets): the work is
+// negligible there and the latency (<= 3 + 5 dependent additions) is what counts.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_axis_tree(AxisJob j0, AxisJob j1) {
+    const AxisJob j = blockIdx.y ? j1 : j0;
+    const uint64_t wid = blockIdx.x * (uint64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (wid >= j.total) return;
+    const uint64_t o = wid >> j.log_inner, i = wid & ((1ull << j.log_inner) - 1);
+    const XYZZ<F>* p = (const XYZZ<F>*)j.in + ((o * j.S) << j.log_inner) + i;
+    XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (uint32_t s = lane; s < j.S; s += 32) { XYZZ<F> v = load_vec(p + ((uint64_t)s << j.log_inner)); acc.add(v); }
+    acc = warp_sum<F>(acc);
+    if (lane == 0) store_vec((XYZZ<F>*)j.out + wid, acc);
 }
 
 // Host plan of the axis-sum levels for one geometry.  Buckets of a window form H = 2^er rows... of 2^m columns
@@ -457,13 +470,13 @@ __host__ inline WsPlan ws_plan(const MsmGeom& g) {
     p.ok = true;
     if (cbits > WS_COL_BITS) { p.m = WS_COL_BITS; p.er = p.m; p.ec = cbits - p.m; p.lenR = 1u << p.ec; p.lenC = 1u << p.m; }
     else { p.lenR = 0; p.lenC = g.B; }
+    // level 0: S = 8 (k_axis_sum, carries the work); level 1: everything left, <= 7 bits (k_axis_tree, one warp per output)
     int rr = p.er, rc = p.ec;
-    while (rr > 0 || rc > 0) {
-        const int l = p.levels++;
-        p.br[l] = rr < 3 ? rr : 3; p.bc[l] = rc < 3 ? rc : 3; rr -= p.br[l]; rc -= p.bc[l];
+    for (int l = 0; l < 2 && (rr > 0 || rc > 0); l++) {
+        p.levels++;
+        p.br[l] = l == 0 ? (rr < 3 ? rr : 3) : rr; p.bc[l] = l == 0 ? (rc < 3 ? rc : 3) : rc; rr -= p.br[l]; rc -= p.bc[l];
         const size_t orow = p.br[l] ? (NW * g.B) >> (p.er - rr) : 0, ocol = p.bc[l] ? (NW * g.B) >> (p.ec - rc) : 0;
-        if (l & 1) { if (orow > p.rowB) p.rowB = orow; if (ocol > p.colB) p.colB = ocol; }
-        else { if (orow > p.rowA) p.rowA = orow; if (ocol > p.colA) p.colA = ocol; }
+        if (l & 1) { p.rowB = orow; p.colB = ocol; } else { p.rowA = orow; p.colA = ocol; }
     }
     p.nR = (p.lenR + 31) / 32; p.nC = (p.lenC + 31) / 32;
     p.tw = 2 * NW * (p.nR + p.nC);
@@ -574,6 +587,10 @@ struct ProfScope {
 struct MsmSorted {
     const uint32_t* keys = nullptr; const uint32_t* vals = nullptr; const uint64_t* counts = nullptr;
     uint64_t n = 0, total = 0; MsmGeom g{};
+    // sorted entries per k_accumulate thread: MSM_SEG, or more when the buckets are dense (hundreds of entries per bucket,
+    // e.g. the 9n-point fflonk commitments): a thread's first run becomes a head partial, and with several heads per
+    // bucket the runs of equal head keys outgrow k_fold_short's parallel path and fall into the serial cascade
+    uint32_t seg = MSM_SEG;
 };
 
 // msm_sort.cu: helpers of the pairing rounds (non-template part)
@@ -620,7 +637,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     size_t o_KB = o_KA + al(ub1 * 4), o_L = o_KB + al(ub1 * 4), o_rest = o_L + al(pthreads * PAIR_K * sizeof(F));
     // size the rest (buckets, heads, partials) for the list that survives the rounds
     uint64_t ub = s.total; for (int r = 0; r < R; r++) ub = (ub + NB + 1) / 2;
-    MsmSorted s2 = s; s2.total = ub; s2.vals = nullptr;
+    MsmSorted s2 = s; s2.total = ub; s2.vals = nullptr; s2.seg = MSM_SEG;
     // first call sizes the whole scratch: probe the tail's requirement with a dry computation (same formula as impl)
     {
         const uint64_t heads0 = (ub + MSM_SEG - 1) / MSM_SEG, heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
@@ -672,7 +689,7 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
     const MsmGeom g = s.g;
     const uint32_t NW = g.windows();
     const uint64_t nbuckets = (uint64_t)NW * g.B;
-    const uint64_t heads0 = (s.total + MSM_SEG - 1) / MSM_SEG;
+    const uint64_t heads0 = (s.total + s.seg - 1) / s.seg;
     const uint64_t heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
     const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
     const uint32_t chunks = g.B / L;
@@ -704,12 +721,12 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
             constexpr bool ext = sizeof(F) > 48 && (sizeof(F) % 64 == 0 || sizeof(F) == 96);
             if constexpr (ext) {
                 switch (g_msm_tuning[0]) {
-                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
-                case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
-                default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
+                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg); break;
+                case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg); break;
+                default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
                 }
             } else {
-                k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);
+                k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg);
             }
             launches++;
         }
@@ -749,11 +766,13 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
             if (wp.br[l]) { rr -= wp.br[l]; jr = AxisJob{rin, rowb[l & 1], (uint64_t)nbuckets >> (wp.er - rr), 1u << wp.br[l], (uint32_t)rr}; rin = rowb[l & 1]; }
             if (wp.bc[l]) { rc -= wp.bc[l]; jc = AxisJob{cin, colb[l & 1], (uint64_t)nbuckets >> (wp.ec - rc), 1u << wp.bc[l], (uint32_t)wp.m}; cin = colb[l & 1]; }
             const uint64_t mx = jr.total > jc.total ? jr.total : jc.total;
-            k_axis_sum<F><<<dim3((unsigned)((mx + 127) / 128), 2), 128, 0, stream>>>(jr, jc); launches++;
+            if (l == 0) k_axis_sum<F><<<dim3((unsigned)((mx + 127) / 128), 2), 128, 0, stream>>>(jr, jc);
+            else k_axis_tree<F><<<dim3((unsigned)((mx + 3) / 4), 2), 128, 0, stream>>>(jr, jc);
+            launches++;
         }
         const uint32_t per = wp.nR + wp.nC;
         k_ws_chunks<F><<<(NW * per + 3) / 4, 128, 0, stream>>>(wp.lenR ? rin : nullptr, wp.lenR, cin, wp.lenC, NW, tw); launches++;
-        k_ws_final<F><<<NW, 128, 5 * sizeof(XYZZ<F>), stream>>>(tw, wp.nR, wp.nC, wp.m, d_wsum); launches++;
+        k_ws_final<F><<<NW, 128, 0, stream>>>(tw, wp.nR, wp.nC, d_wsum); launches++;
     } else if (g.B >= (uint32_t)RED2_BUCKETS && g.B / RED2_BUCKETS <= 1024 && g_msm_tuning[1] == 2) {   // experimental: less work (-36 %) but 2-3x the
         // dependent-add latency of k_reduce; measured slower (proof 27.4 ms vs 26.0 ms overlapped, 31.3 vs 26.6 serialised)
         // hierarchical reduction: per-CTA (R, S) pairs live in the partials area (2 * NC entries per window <= ctas_per_window)

@@ -11,5 +11,8 @@ struct MsmGeom {
     int precomp = 0;
     uint64_t stride = 0, first = 0;
     uint32_t windows() const { return precomp ? 1u : (uint32_t)W; }
+    // points the bucket reduction returns per MSM: every window sum comes back as 5 parts with power-of-two weights
+    // (msm.cuh k_ws_final); the host applies the weights (a few doublings of single points, microseconds on a CPU core)
+    uint32_t wsum_points() const { return 5u * windows(); }
 };
 }

@@ -15,11 +15,23 @@ int SB_FN(buckets)(const void* d_bases, const MsmSorted& s, MsmScratch& scratch,
 }
 void SB_FN(combine)(const uint8_t* wsum_host, const MsmGeom& g, uint8_t* acc_xyzz) {
     PT acc; memcpy(&acc, acc_xyzz, sizeof acc);
-    if (g.precomp) { PT r; memcpy(&r, wsum_host, sizeof r); acc.add(r); }   // single shared bucket set: no Horner
-    else {
-        std::vector<PT> ws(g.W); memcpy(ws.data(), wsum_host, (size_t)g.W * sizeof(PT));
-        msm_combine_host<FT>(ws.data(), g, acc);
-    }
+    const uint32_t NW = g.windows();
+    std::vector<PT> ws(NW);
+    const WsPlan wp = ws_plan(g);
+    if (wp.ok && g_msm_tuning[1] == 0) {
+        // k_ws_final's five parts per window: 2^(m+5) a0 + 2^m a1 + 2^5 a2 + a3 + a4
+        std::vector<PT> parts((size_t)5 * NW); memcpy(parts.data(), wsum_host, parts.size() * sizeof(PT));
+        for (uint32_t w = 0; w < NW; w++) {
+            const PT* a = &parts[(size_t)5 * w];
+            PT t = a[0]; for (int k = 0; k < 5; k++) t = PT::dbl(t);
+            t.add(a[1]); for (int k = 0; k < wp.m; k++) t = PT::dbl(t);
+            PT u = a[2]; for (int k = 0; k < 5; k++) u = PT::dbl(u);
+            u.add(a[3]); u.add(a[4]); t.add(u);
+            ws[w] = t;
+        }
+    } else memcpy(ws.data(), wsum_host, (size_t)NW * sizeof(PT));   // legacy kernels: one point per window
+    if (g.precomp) acc.add(ws[0]);                                   // single shared bucket set: no Horner
+    else msm_combine_host<FT>(ws.data(), g, acc);
     memcpy(acc_xyzz, &acc, sizeof acc);
 }
 void SB_FN(add)(uint8_t* acc_xyzz, const uint8_t* other_xyzz) {

@@ -45,14 +45,14 @@ __global__ void k_digits(const uint8_t* __restrict__ scalars, uint32_t sbytes, u
 }
 
 // number of valid (non-zero-digit) entries = first index whose sorted key is INVALID
-__global__ void k_count_valid(const uint32_t* __restrict__ keys, uint64_t total, uint64_t* __restrict__ out) {
+__global__ void k_count_valid(const uint32_t* __restrict__ keys, uint64_t total, uint64_t* __restrict__ out, uint32_t seg) {
     if (blockIdx.x | threadIdx.x) return;
     uint64_t lo = 0, hi = total;
     while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (keys[mid] == MSM_INVALID_KEY) hi = mid; else lo = mid + 1; }
     out[0] = lo;
     // level sizes for the fold cascade: level 0 always emits ceil(M/SEG) heads; a level >= 1 with
     // <= SEG inputs is the last one (single thread, everything folded into the buckets) and emits none.
-    uint64_t m = (lo + MSM_SEG - 1) / MSM_SEG;
+    uint64_t m = (lo + seg - 1) / seg;
     out[1] = m;
     for (int l = 2; l < 8; l++) { m = (m <= MSM_SEG) ? 0 : (m + MSM_SEG - 1) / MSM_SEG; out[l] = m; }
 }
@@ -123,8 +123,13 @@ int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmG
     cudaError_t e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, kb, vb, (uint64_t)total, 0, end_bit, stream);
     if (e != cudaSuccess) return (int)e;
     launches += 2 + (end_bit + 7) / 8;   // histogram + scan + one onesweep pass per 8 key bits
-    k_count_valid<<<1, 1, 0, stream>>>(kb.Current(), total, counts); launches++;
+    // dense buckets: keep the head partials at <= ~2 per bucket (see MsmSorted::seg)
+    uint32_t seg = MSM_SEG;
+    if (g_msm_tuning[5] >= 0) { const uint64_t avg = nbuckets ? total / nbuckets : 0; while (seg < 256 && avg > 2ull * seg) seg <<= 1; }
+    if (g_msm_tuning[7] > 0) seg = (uint32_t)g_msm_tuning[7];
+    k_count_valid<<<1, 1, 0, stream>>>(kb.Current(), total, counts, seg); launches++;
     prof.end();
+    out->seg = seg;
     out->keys = kb.Current(); out->vals = vb.Current(); out->counts = counts; out->n = n; out->total = total; out->g = g;
     if (stats) stats->launches += launches;
     return (int)cudaGetLastError();

@@ -62,6 +62,32 @@ template <class F> __device__ __forceinline__ void stg_fe(F* p, const F& x) {
     q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
 
+// TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) with an mbarrier transaction count: used to stage the in-tile twiddle
+// table in shared memory once per CTA while the threads are busy with the global loads of the tile.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// bytes: multiple of 16; dst / src 16-byte aligned.  Completion is signalled on `bar` (expect_tx issued here).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+}  // namespace tma
+
+static constexpr uint32_t NTT_WR_BYTES = (1u << (NTT_DMAX - 1)) * 32;   // the in-tile twiddle table w_{2^DMAX}^j, j < 2^(DMAX-1)
+static constexpr size_t NTT_SMEM_EXTRA = NTT_WR_BYTES + 16;             // + the mbarrier
+
 // One Stockham pass.  Fr has 8 limbs for both supported curves.
 // up to 4 independent transforms of the same size per launch (blockIdx.y): Groth16 runs A, B and C together so that the
 // grid fills whole waves (512 CTAs of one 2^20 pass are 1.15 waves at 3 CTAs/SM; 1536 are 3.46)
@@ -76,7 +102,11 @@ k_ntt_pass(NttBatch<F> io, int L, int lgp, int deg, int logc,
     extern __shared__ uint4 ntt_smem[];
     const uint32_t r = 1u << deg, C = 1u << logc, tile = r << logc;
     uint4* slo = ntt_smem; uint4* shi = ntt_smem + tile;
+    uint4* swr = ntt_smem + 2 * tile;                                      // staged copy of tb.wr (TMA bulk copy below)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(swr + NTT_WR_BYTES / 16);
     const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const bool use_wr = deg > 1;                                           // a radix-2 tile has no non-trivial in-tile twiddle
+    if (use_wr && tid == 0) { tma::mbar_init(bar, 1); tma::bulk_g2s(swr, tb.wr, NTT_WR_BYTES, bar); }
     const uint64_t idx0 = (uint64_t)blockIdx.x << logc;
     const uint64_t stride = (1ull << L) >> deg;              // n / r
     const uint64_t pmask = (1ull << lgp) - 1;
@@ -103,6 +133,7 @@ k_ntt_pass(NttBatch<F> io, int L, int lgp, int deg, int logc,
         sts_fe<F>(slo, shi, pos(a, col), x);
     }
     __syncthreads();
+    if (use_wr) tma::mbar_wait(bar, 0);                                    // the twiddle table has landed (it travelled during the loads above)
     // ---- deg radix-2 DIF stages
     const uint32_t nbf = tile >> 1;
     for (int rnd = 0; rnd < deg; rnd++) {
@@ -114,7 +145,7 @@ k_ntt_pass(NttBatch<F> io, int L, int lgp, int deg, int logc,
             uint32_t p0 = pos(i0, col), p1 = pos(i1, col);
             F u0 = lds_fe<F>(slo, shi, p0), u1 = lds_fe<F>(slo, shi, p1);
             F s = F::add(u0, u1), d = F::sub(u0, u1);
-            if (di) d = F::mul(d, ldg_fe<F>(tb.wr + ((uint64_t)(di << rnd) << (NTT_DMAX - deg))));
+            if (di) { const uint32_t wi = (di << rnd) << (NTT_DMAX - deg); d = F::mul(d, lds_fe<F>(swr, swr + 1, 2 * wi)); }
             sts_fe<F>(slo, shi, p0, s);
             sts_fe<F>(slo, shi, p1, d);
         }
@@ -208,7 +239,7 @@ int ntt_run_batch(F* const* a, F* const* b, int count, int L, const NttTables<F>
     for (int i = 0; i < pl.npass; i++) {
         int deg = pl.deg[i], logc = pl.logc[i];
         uint32_t tile = 1u << (deg + logc);
-        size_t smem = (size_t)tile * 32;
+        size_t smem = (size_t)tile * 32 + NTT_SMEM_EXTRA;
         dim3 grid((unsigned)((1ull << L) >> (deg + logc)), (unsigned)count);
         unsigned threads = tile / 2 < (unsigned)NTT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : NTT_THREADS;
         NttBatch<F> io;
@@ -228,7 +259,7 @@ F* ntt_run(F* a, F* b, int L, const NttTables<F>& tb, const NttPre<F>* pre, cons
     return ntt_run_batch<F>(aa, bb, 1, L, tb, pre, post_scale, stream, launches) ? b : a;
 }
 template <class F> inline cudaError_t ntt_configure() {
-    return cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    return cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * 1024 + NTT_SMEM_EXTRA));
 }
 
 }  // namespace sb

@@ -77,11 +77,17 @@ class ProvingKey:
         return self
 
     def prove_raw(self, witness, blinders: bytes) -> bytes:
-        w = _arr(witness)
+        """witness = wtns section 2 ((nVars - nAdditions) x 32 bytes, plain LE), or None to reuse the witness the previous
+        proof on this key left in HBM (sb_fflonk_prove_resident); blinders = 9 x 32 Montgomery bytes."""
         if len(blinders) != 9 * 32:
             raise SbError("blinders must be 9 field elements")
-        out = np.empty(self.curve.lib.sb_fflonk_proof_bytes(self.curve.handle), np.uint8)
-        self.curve.check(self.curve.lib.sb_fflonk_prove(self.curve.handle, self.handle, _ptr(w), w.size // 32, bytes(blinders), _ptr(out)))
+        lib, c = self.curve.lib, self.curve
+        out = np.empty(lib.sb_fflonk_proof_bytes(c.handle), np.uint8)
+        if witness is None:
+            c.check(lib.sb_fflonk_prove_resident(c.handle, self.handle, bytes(blinders), _ptr(out)))
+        else:
+            w = _arr(witness)
+            c.check(lib.sb_fflonk_prove(c.handle, self.handle, _ptr(w), w.size // 32, bytes(blinders), _ptr(out)))
         return out.tobytes()
 
     def release(self):

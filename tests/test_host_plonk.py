@@ -188,3 +188,18 @@ def test_host_flow_with_emulated_ptx_arithmetic(tmp_path, golden):
     rc, err, raw = host_prove(lib, zkey, wtns, BLINDERS)
     assert rc == 0, err
     assert proof_from_bytes(raw) == plonk.plonk_prove(zkey, wtns, BLINDERS)[0]
+
+
+def test_openmp_build_of_the_host_flow_gives_the_same_proof(hostlib):
+    """bench.py's reference arm compiles the same sources with -O3 -fopenmp (bench_plonk.host_flow_lib): the element loops
+    run in parallel, the proof bytes must not change."""
+    import bench_plonk as B
+    gates, adds, n_vars, n_pub, wit = plonk.chain_gates(500)
+    zkey = plonk.plonk_setup_synth(gates, adds, n_vars, n_pub, tau=0xABCDEF0123456789)
+    wtns = plonk.wtns_bytes(wit)
+    rc, err, raw = host_prove(hostlib, zkey, wtns, [7 + i for i in range(11)])
+    assert rc == 0, err
+    _, w = orc.read_wtns(wtns)
+    ci = orc.CURVES[orc.BN254]
+    _, raw_omp = B.cpu_prove("plonk", zkey, np.frombuffer(bytes(w), np.uint8), ci.r, ci.n8q, 4)
+    assert raw_omp == raw
