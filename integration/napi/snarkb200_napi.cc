@@ -2,6 +2,10 @@
 // NOT built or tested in this repository's image (no node / node-addon-api headers here); it is the binding a snarkjs
 // maintainer adds, see INTEGRATION.md.  Build with node-gyp (binding.gyp next to this file).
 //
+// Concurrency: overlapping calls on one context are safe — libsnarkb200 locks the context for the duration of every entry
+// (snarkb200.h "threading"), so AsyncWorkers that land on different libuv threads (joinABC queues one task per 2^22
+// elements before awaiting them, src/groth16_prove.js:328-360) run one after the other instead of racing.
+//
 // Every bulk call runs in a Napi::AsyncWorker so the event loop is never blocked — the reference's methods are async
 // (build/snarkjs.js:14196-14232) — and resolves/rejects a Promise; errors carry sb_last_error() so that messages match
 // the reference's `throw new Error(...)`.
@@ -103,6 +107,32 @@ Napi::Value Groth16Prove(const Napi::CallbackInfo& info) {
   return Queue(info.Env(), c, 8 * n8q, [=](std::vector<uint8_t>& out) { return sb_groth16_prove(c, h, pw, nw, pr, ps, out.data()); }, {w, r, s});
 }
 
+// groth16LoadFile(ctx, path) -> handle: the zkey is streamed from disk through pinned buffers (sb_groth16_load_file), never
+// materialised in the JS heap; groth16ProveWtns(ctx, handle, wtnsFileBytes, r, s, n8q) -> Promise<Buffer(8*n8q)>
+Napi::Value Groth16LoadFile(const Napi::CallbackInfo& info) {
+  sb_ctx* c = ctx_of(info[0]); std::string path = info[1].As<Napi::String>().Utf8Value(); uint64_t h = 0;
+  if (sb_groth16_load_file(c, path.c_str(), &h)) { Napi::Error::New(info.Env(), sb_last_error(c)).ThrowAsJavaScriptException(); return info.Env().Undefined(); }
+  return Napi::Number::New(info.Env(), (double)h);
+}
+Napi::Value Groth16ProveWtns(const Napi::CallbackInfo& info) {
+  sb_ctx* c = ctx_of(info[0]); uint64_t h = (uint64_t)info[1].As<Napi::Number>().Int64Value();
+  auto w = info[2].As<Napi::Uint8Array>(); auto r = info[3].As<Napi::Uint8Array>(); auto s = info[4].As<Napi::Uint8Array>();
+  size_t n8q = info[5].As<Napi::Number>().Uint32Value();
+  size_t wl = w.ByteLength(); const uint8_t *pw = w.Data(), *pr = r.Data(), *ps = s.Data();
+  return Queue(info.Env(), c, 8 * n8q, [=](std::vector<uint8_t>& out) { return sb_groth16_prove_wtns(c, h, pw, wl, pr, ps, out.data()); }, {w, r, s});
+}
+Napi::Value Groth16Info(const Napi::CallbackInfo& info) {
+  uint32_t nv = 0, np = 0, ds = 0;
+  sb_groth16_info(ctx_of(info[0]), (uint64_t)info[1].As<Napi::Number>().Int64Value(), &nv, &np, &ds);
+  Napi::Object o = Napi::Object::New(info.Env());
+  o.Set("nVars", nv); o.Set("nPublic", np); o.Set("domainSize", ds);
+  return o;
+}
+Napi::Value Groth16Release(const Napi::CallbackInfo& info) {
+  sb_groth16_release(ctx_of(info[0]), (uint64_t)info[1].As<Napi::Number>().Int64Value());
+  return info.Env().Undefined();
+}
+
 // plonkLoad / fflonkLoad(ctx, zkeyBytes) -> handle ; plonkProve / fflonkProve(ctx, handle, witnessSection, blinders) -> Promise<Buffer>
 // (src/plonk_prove.js:47, src/fflonk_prove.js:51; blinders = 11 resp. 9 Fr.random() elements concatenated)
 template <int (*LOAD)(sb_ctx*, const uint8_t*, uint64_t, uint64_t*)>
@@ -128,6 +158,10 @@ Napi::Object Init(Napi::Env env, Napi::Object exports) {
   exports.Set("qapJoinAbc", Napi::Function::New(env, QapJoinAbc));
   exports.Set("groth16Load", Napi::Function::New(env, Groth16Load));
   exports.Set("groth16Prove", Napi::Function::New(env, Groth16Prove));
+  exports.Set("groth16LoadFile", Napi::Function::New(env, Groth16LoadFile));
+  exports.Set("groth16ProveWtns", Napi::Function::New(env, Groth16ProveWtns));
+  exports.Set("groth16Info", Napi::Function::New(env, Groth16Info));
+  exports.Set("groth16Release", Napi::Function::New(env, Groth16Release));
   exports.Set("plonkLoad", Napi::Function::New(env, KeyLoad<sb_plonk_load>));
   exports.Set("plonkProve", Napi::Function::New(env, KeyProve<sb_plonk_prove, sb_plonk_proof_bytes>));
   exports.Set("fflonkLoad", Napi::Function::New(env, KeyLoad<sb_fflonk_load>));

@@ -103,12 +103,32 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def _prefer_bundled_nccl():
+    """libsnarkb200 dlopens libnccl.so.2 on first multi-GPU use (SB_NCCL_LIB first).  In a Python process that also imports
+    torch, torch's bundled libnccl (a newer build under the same soname) must be the copy in the process: the first one
+    loaded wins, and torch cannot import against an older system copy.  Point the library at the bundled file unless the
+    caller chose one; a Node host has no torch and uses the system libnccl."""
+    if os.environ.get("SB_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["SB_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C snarkjs_b200/csrc` "
                                "(there is no CPU fallback)")
+        _prefer_bundled_nccl()
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)           # raises AttributeError if a declared symbol is not exported

@@ -28,6 +28,7 @@ static constexpr int MSM_SEG = 32;          // sorted entries per thread in k_ac
 static constexpr int MSM_ACC_THREADS = 128;
 static constexpr int MSM_RED_CHUNK = 16;    // buckets per thread in k_reduce
 static constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
+static constexpr int MSM_COUNTS_SEG = 8;      // counts[8]: sorted entries per k_accumulate thread (counts[0] = valid entries, [1..7] = fold level sizes)
 
 
 // Window-size choice.  Cost model: W_eff*n mixed adds (10 modmul) + one pass over the buckets (~60 modmul each);
@@ -108,8 +109,9 @@ template <class F, int MINB>
 __global__ void __launch_bounds__(MSM_ACC_THREADS, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const uint64_t* __restrict__ counts, XYZZ<F>* __restrict__ buckets,
-             XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys, uint32_t seg) {
+             XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
     const uint64_t M = counts[0];
+    const uint32_t seg = (uint32_t)counts[MSM_COUNTS_SEG];          // entries per thread, fitted to whole waves by k_count_valid
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint64_t lo = t * seg;
     if (lo >= M) return;
@@ -587,10 +589,15 @@ struct ProfScope {
 struct MsmSorted {
     const uint32_t* keys = nullptr; const uint32_t* vals = nullptr; const uint64_t* counts = nullptr;
     uint64_t n = 0, total = 0; MsmGeom g{};
-    // sorted entries per k_accumulate thread: MSM_SEG, or more when the buckets are dense (hundreds of entries per bucket,
-    // e.g. the 9n-point fflonk commitments): a thread's first run becomes a head partial, and with several heads per
-    // bucket the runs of equal head keys outgrow k_fold_short's parallel path and fall into the serial cascade
-    uint32_t seg = MSM_SEG;
+    // Sorted entries per k_accumulate thread.  The target is MSM_SEG, or more when the buckets are dense (hundreds of entries
+    // per bucket, e.g. the 9n-point fflonk commitments: a thread's first run becomes a head partial, and with several heads
+    // per bucket the runs of equal head keys outgrow k_fold_short's parallel path).  The actual value is chosen on the
+    // device (k_count_valid, counts[MSM_COUNTS_SEG]) once the number of valid entries M is known: every thread does the same
+    // work, so the kernel time is waves x seg, and seg = ceil(M / (k * resident threads)) makes the grid exactly k full waves
+    // of the 148 SMs instead of k - 1 waves and a fraction (applied for k <= 3: shards of a multi-GPU proof, small MSMs;
+    // measured on the 2-GPU shards: G1 accumulation -7.5 %, G2 -10.6 %; with more waves the effect vanishes).  seg_lo = the smallest value the device may pick (grid and
+    // head-buffer sizing on the host).
+    uint32_t seg_lo = MSM_SEG;
 };
 
 // msm_sort.cu: helpers of the pairing rounds (non-template part)
@@ -637,7 +644,7 @@ int msm_buckets(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& scratc
     size_t o_KB = o_KA + al(ub1 * 4), o_L = o_KB + al(ub1 * 4), o_rest = o_L + al(pthreads * PAIR_K * sizeof(F));
     // size the rest (buckets, heads, partials) for the list that survives the rounds
     uint64_t ub = s.total; for (int r = 0; r < R; r++) ub = (ub + NB + 1) / 2;
-    MsmSorted s2 = s; s2.total = ub; s2.vals = nullptr; s2.seg = MSM_SEG;
+    MsmSorted s2 = s; s2.total = ub; s2.vals = nullptr; s2.seg_lo = MSM_SEG;
     // first call sizes the whole scratch: probe the tail's requirement with a dry computation (same formula as impl)
     {
         const uint64_t heads0 = (ub + MSM_SEG - 1) / MSM_SEG, heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
@@ -689,7 +696,7 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
     const MsmGeom g = s.g;
     const uint32_t NW = g.windows();
     const uint64_t nbuckets = (uint64_t)NW * g.B;
-    const uint64_t heads0 = (s.total + s.seg - 1) / s.seg;
+    const uint64_t heads0 = (s.total + s.seg_lo - 1) / s.seg_lo;   // upper bound; the device knows the exact count (counts[1])
     const uint64_t heads1 = (heads0 + MSM_SEG - 1) / MSM_SEG;
     const uint32_t L = g.B < (uint32_t)MSM_RED_CHUNK ? g.B : MSM_RED_CHUNK;
     const uint32_t chunks = g.B / L;
@@ -721,12 +728,12 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
             constexpr bool ext = sizeof(F) > 48 && (sizeof(F) % 64 == 0 || sizeof(F) == 96);
             if constexpr (ext) {
                 switch (g_msm_tuning[0]) {
-                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg); break;
-                case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg); break;
-                default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
+                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
                 }
             } else {
-                k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA, s.seg);
+                k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);
             }
             launches++;
         }

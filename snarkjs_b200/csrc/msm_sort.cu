@@ -44,14 +44,23 @@ __global__ void k_digits(const uint8_t* __restrict__ scalars, uint32_t sbytes, u
     }
 }
 
-// number of valid (non-zero-digit) entries = first index whose sorted key is INVALID
-__global__ void k_count_valid(const uint32_t* __restrict__ keys, uint64_t total, uint64_t* __restrict__ out, uint32_t seg) {
+// number of valid (non-zero-digit) entries = first index whose sorted key is INVALID; then the entries per accumulation
+// thread: target T, fitted so that the grid is a whole number of waves of `wave` resident threads (MsmSorted comment).
+__global__ void k_count_valid(const uint32_t* __restrict__ keys, uint64_t total, uint64_t* __restrict__ out, uint32_t T, uint32_t seg_lo, uint64_t wave) {
     if (blockIdx.x | threadIdx.x) return;
     uint64_t lo = 0, hi = total;
     while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (keys[mid] == MSM_INVALID_KEY) hi = mid; else lo = mid + 1; }
     out[0] = lo;
-    // level sizes for the fold cascade: level 0 always emits ceil(M/SEG) heads; a level >= 1 with
-    // <= SEG inputs is the last one (single thread, everything folded into the buckets) and emits none.
+    uint64_t seg = T;
+    if (wave) {
+        const uint64_t k = (lo + wave * T - 1) / (wave * T);             // waves at the target size
+        if (k && k <= 3) seg = (lo + k * wave - 1) / (k * wave);      // with 4+ waves the partial last wave still saturates the pipe (measured: no gain, more heads)
+        if (seg < seg_lo) seg = seg_lo;
+        if (seg > T) seg = T;
+    }
+    out[MSM_COUNTS_SEG] = seg;
+    // level sizes for the fold cascade: level 0 always emits ceil(M/seg) heads; a level >= 1 with
+    // <= MSM_SEG inputs is the last one (single thread, everything folded into the buckets) and emits none.
     uint64_t m = (lo + seg - 1) / seg;
     out[1] = m;
     for (int l = 2; l < 8; l++) { m = (m <= MSM_SEG) ? 0 : (m + MSM_SEG - 1) / MSM_SEG; out[l] = m; }
@@ -78,6 +87,7 @@ __global__ void k_counts_from_offsets(const uint32_t* __restrict__ off, uint32_t
     counts[0] = m;
     m = (m + MSM_SEG - 1) / MSM_SEG; counts[1] = m;
     for (int l = 2; l < 8; l++) { m = (m <= (uint64_t)MSM_SEG) ? 0 : (m + MSM_SEG - 1) / MSM_SEG; counts[l] = m; }
+    counts[MSM_COUNTS_SEG] = MSM_SEG;
 }
 size_t msm_pair_scan_tmp_bytes(uint32_t NB) {
     size_t bytes = 0;
@@ -123,13 +133,18 @@ int msm_sort_entries(const uint8_t* d_scalars, uint32_t sbytes, uint64_t n, MsmG
     cudaError_t e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, kb, vb, (uint64_t)total, 0, end_bit, stream);
     if (e != cudaSuccess) return (int)e;
     launches += 2 + (end_bit + 7) / 8;   // histogram + scan + one onesweep pass per 8 key bits
-    // dense buckets: keep the head partials at <= ~2 per bucket (see MsmSorted::seg)
-    uint32_t seg = MSM_SEG;
-    if (g_msm_tuning[5] >= 0) { const uint64_t avg = nbuckets ? total / nbuckets : 0; while (seg < 256 && avg > 2ull * seg) seg <<= 1; }
-    if (g_msm_tuning[7] > 0) seg = (uint32_t)g_msm_tuning[7];
-    k_count_valid<<<1, 1, 0, stream>>>(kb.Current(), total, counts, seg); launches++;
+    // target entries per thread: dense buckets keep the head partials at <= ~2 per bucket; then whole-wave fitting on the device
+    uint32_t T = MSM_SEG;
+    const bool adaptive = g_msm_tuning[5] >= 0 && g_msm_tuning[7] <= 0;
+    if (adaptive) { const uint64_t avg = nbuckets ? total / nbuckets : 0; while (T < 256 && avg > 2ull * T) T <<= 1; }
+    if (g_msm_tuning[7] > 0) T = (uint32_t)g_msm_tuning[7];
+    static int sm_count = 0;
+    if (!sm_count) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148; }
+    const uint64_t wave = adaptive ? (uint64_t)sm_count * 4 * MSM_ACC_THREADS : 0;     // 4 CTAs of 128 threads per SM (2 for the extension-field kernels: same fit)
+    const uint32_t seg_lo = adaptive ? (T == (uint32_t)MSM_SEG ? 16u : T / 2) : T;
+    k_count_valid<<<1, 1, 0, stream>>>(kb.Current(), total, counts, T, seg_lo, wave); launches++;
     prof.end();
-    out->seg = seg;
+    out->seg_lo = seg_lo;
     out->keys = kb.Current(); out->vals = vb.Current(); out->counts = counts; out->n = n; out->total = total; out->g = g;
     if (stats) stats->launches += launches;
     return (int)cudaGetLastError();
