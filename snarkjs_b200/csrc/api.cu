@@ -717,6 +717,7 @@ int sb_set_tuning(int key, int value) {
     if (key == 8) { g_stage_enabled = value; return 0; }                                                      // pinned staging of pageable buffers
     if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
     if (key == 9) { g_msm_tuning[7] = value; return 0; }                                                      // forced entries per accumulation thread (0 = adaptive)
+    if (key == 10) { g_msm_tuning[8] = value; return 0; }                                                     // minBlocksPerSM variant of the 12-limb base-field accumulation (BLS12-381 G1)
     if (key < 0 || key >= 7) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;
 }
 double sb_last_stat(sb_ctx* c, int which) { SB_LOCK(c); return (c && which >= 0 && which < 16) ? c->stat[which] : 0.0; }

@@ -566,7 +566,7 @@ struct MsmScratch {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-extern int g_msm_tuning[8];
+extern int g_msm_tuning[12];
 
 struct MsmLaunchStats {
     int launches = 0;
@@ -731,6 +731,15 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
                 case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
+                }
+            } else if constexpr (sizeof(F) > 32) {
+                // 12-limb base field (BLS12-381 G1): at 4 CTAs/SM the 128-register cap spills ~50 words of the mixed addition
+                // (ptxas: 218 B spill stores / 188 B loads); 3 CTAs/SM (168 registers) and 2 (190) do not spill.
+                // sb_set_tuning(10, minBlocksPerSM) selects the variant, 0 = default.
+                switch (g_msm_tuning[8]) {
+                case 2: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                default: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 }
             } else {
                 k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);

@@ -5,7 +5,7 @@
 
 namespace sb {
 
-int g_msm_tuning[8] = {0};
+int g_msm_tuning[12] = {0};
 
 // ------------------------------------------------------------------------------------------------
 // digits: thread i recodes scalar i into W signed digits (reference _getChunk extracts unsigned chunks;
