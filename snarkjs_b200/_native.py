@@ -135,4 +135,10 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        # experiment selection without code changes: SB_TUNE="key=value,key=value" -> sb_set_tuning (kernel variants only:
+        # every variant computes the same bytes)
+        for kv in filter(None, os.environ.get("SB_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            if L.sb_set_tuning(int(k), int(v)) != 0:
+                raise RuntimeError(f"SB_TUNE: sb_set_tuning({k}, {v}) rejected")
     return _lib

@@ -138,6 +138,59 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ k
     else store_vec(buckets + cur, acc);
 }
 
+// The same walk for an extension-field group with every point spread over a lane pair (Fp2L, ec.cuh): thread 2t holds the c0
+// components of segment t's accumulator, thread 2t+1 the c1 components.  Half the registers per thread (the plain kernel needs
+// 252 and runs 8 warps per SM), twice the threads; the arithmetic per point is the same 16 dual products + 4 multiplies, split
+// evenly over the two lanes.  Memory layout is unchanged (x.c0 x.c1 y.c0 y.c1 zz.c0 ...): lane `par` moves the blocks 2k + par.
+template <class T> struct fp2_param;
+template <class P> struct fp2_param<Fp2<P>> { typedef P type; };
+template <class P, int MINB>
+__global__ void __launch_bounds__(MSM_ACC_THREADS, MINB)
+k_accumulate_pair(const Affine<Fp2<P>>* __restrict__ bases, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                  const uint64_t* __restrict__ counts, XYZZ<Fp2<P>>* __restrict__ buckets,
+                  XYZZ<Fp2<P>>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
+    typedef Fp2L<P> F; typedef Fp<P> B;
+    const uint64_t M = counts[0];
+    const uint32_t seg = (uint32_t)counts[MSM_COUNTS_SEG];
+    const uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 1;
+    const uint32_t par = threadIdx.x & 1u;
+    uint64_t lo = t * seg;
+    if (lo >= M) return;                                     // both lanes of a pair leave together
+    uint64_t hi = lo + seg < M ? lo + seg : M;
+    const F one = F::one();
+    XYZZ<F> acc = XYZZ<F>::inf();
+    auto put = [&](XYZZ<Fp2<P>>* dst, const XYZZ<F>& a) {
+        B* q = reinterpret_cast<B*>(dst);
+        store_vec(q + par, a.x.m); store_vec(q + 2 + par, a.y.m); store_vec(q + 4 + par, a.zz.m); store_vec(q + 6 + par, a.zzz.m);
+    };
+    uint32_t cur = keys[lo];
+    bool first = true;
+    for (uint64_t e = lo; e < hi; e++) {
+        uint32_t k = keys[e], v = vals ? vals[e] : (uint32_t)e;
+        if (k != cur) {
+            if (first) { put(heads + t, acc); if (!par) head_keys[t] = cur; first = false; }
+            else put(buckets + cur, acc);
+            acc = XYZZ<F>::inf(); cur = k;
+        }
+        F px, py;
+        {
+            constexpr int NV = sizeof(B) / 16;
+            const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const B*>(bases + (v & 0x7fffffffu)) + par);
+            uint4* dx = reinterpret_cast<uint4*>(&px.m); uint4* dy = reinterpret_cast<uint4*>(&py.m);
+#pragma unroll
+            for (int i = 0; i < NV; i++) dx[i] = __ldg(p + i);
+#pragma unroll
+            for (int i = 0; i < NV; i++) dy[i] = __ldg(p + 2 * NV + i);
+        }
+        if (!(px.is_zero() & py.is_zero())) {
+            py = F::cneg(py, (v >> 31) != 0);
+            acc.add_affine(px, py, one);
+        }
+    }
+    if (first) { put(heads + t, acc); if (!par) head_keys[t] = cur; }
+    else put(buckets + cur, acc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // level 1 fast path: one thread per head partial.  Heads are sorted by key; a run of equal keys of length
 // <= MSM_SHORT_RUN is summed by its first thread and added to the bucket (for uniform scalars practically every
@@ -727,7 +780,11 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
             // extension-field groups (accumulator = 64-96 registers) have their own variants
             constexpr bool ext = sizeof(F) > 48 && (sizeof(F) % 64 == 0 || sizeof(F) == 96);
             if constexpr (ext) {
-                switch (g_msm_tuning[0]) {
+                typedef typename fp2_param<F>::type FP;
+                const unsigned pgrid = (unsigned)((2 * heads0 + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+                if (g_msm_tuning[9] == 4) k_accumulate_pair<FP, 4><<<pgrid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);
+                else if (g_msm_tuning[9] == 3) k_accumulate_pair<FP, 3><<<pgrid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);
+                else switch (g_msm_tuning[0]) {
                 case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
