@@ -717,6 +717,7 @@ int sb_set_tuning(int key, int value) {
     if (key == 8) { g_stage_enabled = value; return 0; }                                                      // pinned staging of pageable buffers
     if (key == 7) { if (value < 10 || value > 12) return SB_ERR_ARG; g_ntt_tile_log = value; return 0; }   // NTT tile size
     if (key == 9) { g_msm_tuning[7] = value; return 0; }                                                      // forced entries per accumulation thread (0 = adaptive)
+    if (key == 12) { g_msm_tuning[10] = value; return 0; }                                                    // minBlocksPerSM variant of the 8-limb base-field accumulation (BN254 G1): 4 default, 3, 2
     if (key == 11) { g_msm_tuning[9] = value; return 0; }                                                     // lane-pair G2 accumulation (k_accumulate_pair): 0 = off, 3 / 4 = minBlocksPerSM
     if (key == 10) { g_msm_tuning[8] = value; return 0; }                                                     // minBlocksPerSM variant of the 12-limb base-field accumulation (BLS12-381 G1)
     if (key < 0 || key >= 7) return SB_ERR_ARG; g_msm_tuning[key] = value; return 0;

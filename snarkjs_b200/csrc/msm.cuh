@@ -790,16 +790,22 @@ int msm_buckets_impl(const Affine<F>* d_bases, const MsmSorted& s, MsmScratch& s
                 default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;   // measured best: 8.0 ms vs 8.5 (2^20 G2)
                 }
             } else if constexpr (sizeof(F) > 32) {
-                // 12-limb base field (BLS12-381 G1): at 4 CTAs/SM the 128-register cap spills ~50 words of the mixed addition
-                // (ptxas: 218 B spill stores / 188 B loads); 3 CTAs/SM (168 registers) and 2 (190) do not spill.
-                // sb_set_tuning(10, minBlocksPerSM) selects the variant, 0 = default.
+                // 12-limb base field (BLS12-381 G1).  At 4 CTAs/SM the 128-register cap spills ~50 words of the mixed addition
+                // (ptxas: 218 B spill stores / 188 B loads); 3 CTAs/SM (168 registers) and 2 (190) do not spill.  Measured on the
+                // B200 (PLONK 2^18, nine accumulations): 2 CTAs/SM 15.8 ms, 4 CTAs/SM 16.7 ms, 3 CTAs/SM 19.3 ms
+                // (profiles/ab_r2_summary.txt) -> 2 is the default; sb_set_tuning(10, 3 | 4) selects the others.
                 switch (g_msm_tuning[8]) {
-                case 2: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                case 4: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
-                default: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                default: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
                 }
             } else {
-                k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA);
+                // 8-limb base field (BN254 G1): 122 registers at 4 CTAs/SM, no spills; sb_set_tuning(12, 3 | 2) = lower-occupancy builds
+                switch (g_msm_tuning[10]) {
+                case 3: k_accumulate<F, 3><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                case 2: k_accumulate<F, 2><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                default: k_accumulate<F, 4><<<grid, MSM_ACC_THREADS, 0, stream>>>(d_bases, s.keys, s.vals, s.counts, buckets, headsA, hkA); break;
+                }
             }
             launches++;
         }
