@@ -50,3 +50,62 @@ def test_resident_needs_a_witness():
         pk.release()
     finally:
         curve.terminate()
+
+
+@pytest.mark.parametrize("proto,cname,L", [("plonk", "bls12381", 18), ("fflonk", "bn128", 18), ("plonk", "bls12381", 20), ("fflonk", "bn128", 20)])
+def test_bench_workload_at_config_size_matches_committed_cpu_hash(proto, cname, L):
+    """BASELINE config #5 at 2^18 and at its stated size 2^20: the proof of the bench key equals the CPU port's, through
+    the hash the CPU port committed (tests/golden/bench_proof_hashes.json, made by make_bench_hashes.py; the port needs
+    40 s per 2^20 proof, so it is not re-run here), from a host witness and from the resident one."""
+    import snarkjs_b200
+    from snarkjs_b200 import fflonk, plonk, synth
+    import bench_plonk as B
+    from bench import proof_hash
+    want = B.golden_hash(proto, cname, L)
+    assert want, "no committed hash for this workload"
+    curve = snarkjs_b200.getCurveFromName(cname)
+    try:
+        zkey, wit = (synth.synth_plonk_zkey if proto == "plonk" else synth.synth_fflonk_zkey)(curve, L)
+        mod = plonk if proto == "plonk" else fflonk
+        pk = mod.ProvingKey(zkey, curve)
+        del zkey
+        bl = B._blinders(curve.r, proto)
+        raw = pk.prove_raw(wit, bl)
+        assert proof_hash(mod.proof_to_object(curve, raw)) == want
+        assert pk.prove_raw(None, bl) == raw
+        pk.release()
+    finally:
+        curve.terminate()
+
+
+def test_groth16_2_20_eight_point_range_shards_match_oracle_hash():
+    """BASELINE config #4's layout at the benchmark size on one device: the 2^20 bench key loaded as eight point-range
+    shards (each with its own window tables, 1/8 of the key per load), every shard's five partial MSMs, the gathered
+    partials finished to the proof -- which must be the CPU oracle's proof of this key (committed hash) and the unsharded
+    key's proof."""
+    import snarkjs_b200
+    from snarkjs_b200 import groth16, synth
+    from bench import golden_hash, proof_hash
+    L, NS = 20, 8
+    want = golden_hash("groth16", "bn128", L, False)
+    assert want
+    curve = snarkjs_b200.getCurveFromName("bn128")
+    try:
+        zkey = synth.synth_groth16_zkey(curve, L, seed=1)
+        w = synth.chain_witness(curve.r, L)
+        r = (5 * (1 << 256) % curve.r).to_bytes(32, "little")
+        s = (7 * (1 << 256) % curve.r).to_bytes(32, "little")
+        parts = []
+        for i in range(NS):                       # one shard resident at a time: what one GPU of eight holds
+            k = groth16.ProvingKey(zkey, curve=curve, shard=i, n_shards=NS)
+            parts.append(np.array(k.prove_shard(w, i, NS), copy=True))
+            if i < NS - 1:
+                k.release()
+        proof = k.finish(np.concatenate(parts), NS, r, s)
+        k.release()
+        assert proof_hash(groth16.proof_to_object(curve, proof)) == want
+        full = groth16.ProvingKey(zkey, curve=curve)
+        assert full.prove_raw(w, r, s) == proof
+        full.release()
+    finally:
+        curve.terminate()
