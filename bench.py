@@ -122,6 +122,14 @@ def golden_hash(workload: str, curve: str, L: int, witness_like: bool):
         return None
 
 
+def workload_config(L: int, world: int, witness_like: bool) -> dict:
+    """`config` of the JSON line; the B200 arm and the reference arm print the same dictionary for the same flags."""
+    return {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{L} (nVars 2^{L}, {2 * ((1 << L) - 3) + 2} QAP coefficients); 4 G1 MSM + 1 G2 MSM of 2^{L} points, 6 NTT of 2^{L}",
+            "curve": "bn128", "witness": "witness-like (50% zeros, 25% ones)" if witness_like else "uniform field elements (chain circuit)",
+            "parallelism": f"one proof over {world} GPUs: MSM point-range shards, A/B/C transform chains on ranks 0..2, NCCL exchange inside the library" if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (384 MiB of bases + 32 MiB witness per proof vs 126 MB L2)"}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
 def oracle_groth16(log_n: int, steps: int, warmup: int, zkey: bytes | None = None, witness: np.ndarray | None = None):
     """Times the oracle's restatement of groth16_prove.js (reference algorithms: pTSizes Pippenger, radix-2 DIT NTT,
@@ -167,10 +175,9 @@ def run_reference(args):
     ph = proof_hash(proof)
     gold = golden_hash("groth16", "bn128", L, False)
     line = {"metric": "groth16_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+            "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "weak" if args.mode == "replicas" else "strong", "vs_baseline": None,
             "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{args.log_n}", "curve": "bn128",
-                       "same_key_as_b200_arm": True},
+            "config": workload_config(args.log_n, args.gpus, False), "same_key_as_b200_arm": True,
             "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample, "nproc": os.cpu_count()},
             "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "proof_sha256": ph, "oracle_match": (ph == gold) if gold else None}
@@ -342,11 +349,9 @@ def run_b200(args):
     line = {
         "metric": "groth16_proofs_per_sec", "value": args.steps / dt_res, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dt_res / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "scaling": "weak" if args.mode == "replicas" else "strong", "vs_baseline": None,   # one label for the whole 1..N sweep: the sharded proof is the same total work at every N
         "dtype": "u32x8 (256-bit modular integers, 32-bit limbs)", "data": "synthetic",
-        "config": {"workload": f"groth16 prove, BN254, synthetic chain R1CS, domain 2^{L} (nVars 2^{L}, {2 * ((1 << L) - 3) + 2} QAP coefficients); 4 G1 MSM + 1 G2 MSM of 2^{L} points, 6 NTT of 2^{L}",
-                   "curve": "bn128", "witness": "witness-like (50% zeros, 25% ones)" if args.witness_like else "uniform field elements (chain circuit)", "parallelism": f"one proof over {world} GPUs: MSM point-range shards, A/B/C transform chains on ranks 0..2, NCCL exchange inside the library" if world > 1 else "single GPU",
-                   "l2_policy": "inputs larger than L2 (384 MiB of bases + 32 MiB witness per proof vs 126 MB L2)"},
+        "config": workload_config(L, world, args.witness_like),
         "e2e": {"value": args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": int(nwit * 32), "d2h_bytes_per_step": int(proof.size),
                 "ms_per_step": dt_e2e / args.steps * 1e3, "api": ("sb_groth16_prove_dist (pinned host witness on every rank, 1/N uploaded per rank -> affine proof bytes on rank 0's host)" if world > 1 else "sb_groth16_prove (pinned host witness -> affine proof bytes on host)")},
         "gpu_launches": int(l1 - l0),
