@@ -19,7 +19,8 @@ stops verifying when a commitment, an evaluation or the public signal is perturb
 different reference files.  The reference ships no fflonk proof and draws its blinders at random (:321-324), so the
 prover's bytes are not pinned directly: "partially pinned", as oracle/plonk.py.
 
-Field elements are plain ints in [0, r); bulk NTT / MSM go through the C++ restatement.  BN254 only (pairing).
+Field elements are plain ints in [0, r); bulk NTT / MSM go through the C++ restatement.  BN254 only (pairing: oracle.py's,
+pinned to the reference's known-answer vectors by tests/test_oracle_keypair_kat.py).
 """
 from __future__ import annotations
 

@@ -26,6 +26,8 @@ Pins (tests/test_oracle_plonk.py), and what is NOT pinned:
     from plonk_setup_synth.  Prover and verifier restate two different reference files (plonk_prove.js /
     plonk_verify.js), so algebra slips show up as a failed verification.
   * the NTT / MSM primitives underneath are pinned byte-for-byte by the zkey sections (tests/test_oracle_golden.py).
+  * the BN254 pairing the verifier ends in is pinned to the reference's hard-coded known-answer vectors
+    (test/keypar_test.js via oracle/keypair.py, tests/test_oracle_keypair_kat.py).
   * the transcript's byte layout (32-byte big-endian words: Qm.x, Qm.y, ..., S3.y, the public signals, A, B, C; then
     beta -> gamma; beta, gamma, Z -> alpha; alpha, T1..T3 -> xi; xi, 6 evaluations -> v; Wxi, Wxiw -> u; keccak256
     reduced mod r) is stated a third time, independently, by the reference's current Solidity template
